@@ -1,0 +1,499 @@
+// capi.cu -- C-ABI (include/rtpbr.h) over the CUDA kernels.  One context = one GPU, one
+// stream, all device memory.  No CPU fallback: every compute call needs a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rtpbr.h"
+#include "host_setup.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(RTPBR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+// ---- NCCL, resolved at run time so the library loads on machines without it -------------
+struct UniqueId { char internal[128]; };   // == ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId /* by value */, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string& why)
+{
+    if (g_nccl.handle) return true;
+    const char* names[] = { getenv("RTPBR_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+    void* h = nullptr;
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { why = "cannot dlopen libnccl.so.2 (set RTPBR_NCCL_LIB)"; return false; }
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.Reduce = (decltype(g_nccl.Reduce))dlsym(h, "ncclReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Reduce || !g_nccl.CommDestroy) {
+        why = "libnccl is missing required symbols";
+        return false;
+    }
+    g_nccl.handle = h;
+    return true;
+}
+
+}  // namespace
+
+struct RtpbrContext {
+    RtpbrConfig cfg{};
+    RtpbrCamera cam{};
+    rt::KParams P{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;  // pool
+    size_t kernel_events_used = 0;
+    float4* d_image_buffer = nullptr;
+    float* d_image_pixels = nullptr;
+    float* d_rr = nullptr;
+    float* d_env = nullptr;
+    unsigned int* d_work = nullptr;
+    unsigned long long* d_counters = nullptr;
+    bool have_scene = false, have_camera = false;
+    uint32_t sample_base = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0, blocks_per_sm = 0;
+    void* nccl_comm = nullptr;
+    int nccl_rank = 0, nccl_nranks = 1;
+    unsigned long long launches = 0;
+};
+
+namespace {
+
+size_t npixels(const RtpbrContext* c) { return (size_t)c->cfg.width * (size_t)c->cfg.height; }
+
+rt::KernelSelect select_kernel(const RtpbrContext* c)
+{
+    rt::KernelSelect s;
+    s.family = c->cfg.family;
+    s.nobj = c->P.nobj;
+    s.count = c->cfg.count_work != 0;
+    return s;
+}
+
+int validate_config(const RtpbrConfig& c)
+{
+    if (c.width < 1 || c.height < 1 || c.width > 65536 || c.height > 65536) return fail(RTPBR_ERR_ARG, "bad resolution");
+    if ((uint64_t)c.width * (uint64_t)c.height > (1ull << 30)) return fail(RTPBR_ERR_ARG, "resolution too large");
+    if (c.family < RTPBR_FAMILY_A || c.family > RTPBR_FAMILY_C) return fail(RTPBR_ERR_ARG, "bad family");
+    if (c.max_bounces < 1 || c.max_bounces > RTPBR_MAX_BOUNCES) return fail(RTPBR_ERR_ARG, "bad max_bounces");
+    if (c.max_steps < 1) return fail(RTPBR_ERR_ARG, "bad max_steps");
+    if (!(c.light_quality > 0.f)) return fail(RTPBR_ERR_ARG, "bad light_quality");
+    if (c.family != RTPBR_FAMILY_A) return fail(RTPBR_ERR_UNSUPPORTED, "only family A is implemented in this build");
+    return RTPBR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtpbr_last_error(void) { return g_last_error.c_str(); }
+int rtpbr_version(void) { return RTPBR_VERSION; }
+int rtpbr_sizeof_config(void) { return (int)sizeof(RtpbrConfig); }
+int rtpbr_sizeof_object(void) { return (int)sizeof(RtpbrObject); }
+int rtpbr_sizeof_camera(void) { return (int)sizeof(RtpbrCamera); }
+
+int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
+{
+    if (!cfg || !out) return fail(RTPBR_ERR_ARG, "null argument");
+    *out = nullptr;
+    int rc = validate_config(*cfg);
+    if (rc != RTPBR_OK) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(RTPBR_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                        " (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(RTPBR_ERR_ARG, "bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RTPBR_ERR_CUDA, "librtpbr is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                                        std::to_string(prop.minor));
+    RtpbrContext* c = new (std::nothrow) RtpbrContext();
+    if (!c) return fail(RTPBR_ERR_ARG, "out of host memory");
+    c->cfg = *cfg;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    rt::fill_config(c->P, c->cfg);
+    rt::fill_shard(c->P, 0, 1, 32);
+    c->P.resolve_q = 8;
+    if (const char* q = getenv("RTPBR_RESOLVE_Q")) {
+        int v = atoi(q);
+        if (v >= 1 && v <= 32) c->P.resolve_q = v;
+    }
+#define CREATE_TRY(expr)                                                                            \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            rtpbr_destroy(c);                                                                       \
+            return fail(RTPBR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+        }                                                                                           \
+    } while (0)
+    CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreate(&c->ev_start));
+    CREATE_TRY(cudaEventCreate(&c->ev_stop));
+    const size_t n = npixels(c);
+    CREATE_TRY(cudaMalloc(&c->d_image_buffer, n * sizeof(float4)));
+    CREATE_TRY(cudaMalloc(&c->d_image_pixels, n * 3 * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&c->d_work, sizeof(unsigned int)));
+    CREATE_TRY(cudaMalloc(&c->d_counters, RTPBR_CNT_COUNT * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemsetAsync(c->d_image_buffer, 0, n * sizeof(float4), c->stream));
+    CREATE_TRY(cudaMemsetAsync(c->d_image_pixels, 0, n * 3 * sizeof(float), c->stream));
+    CREATE_TRY(cudaMemsetAsync(c->d_counters, 0, RTPBR_CNT_COUNT * sizeof(unsigned long long), c->stream));
+    std::vector<float> rr = rt::rr_table(c->cfg);
+    CREATE_TRY(cudaMalloc(&c->d_rr, rr.size() * sizeof(float)));
+    CREATE_TRY(cudaMemcpyAsync(c->d_rr, rr.data(), rr.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CREATE_TRY(cudaStreamSynchronize(c->stream));
+#undef CREATE_TRY
+    c->P.image_buffer = c->d_image_buffer;
+    c->P.rr_prob = c->d_rr;
+    c->P.env = nullptr;
+    c->P.env_w = c->P.env_h = 0;
+    c->P.work_counter = c->d_work;
+    c->P.counters = c->d_counters;
+    *out = c;
+    return RTPBR_OK;
+}
+
+int rtpbr_destroy(RtpbrContext* c)
+{
+    if (!c) return RTPBR_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    for (auto& p : c->kernel_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+    cudaFree(c->d_image_buffer);
+    cudaFree(c->d_image_pixels);
+    cudaFree(c->d_rr);
+    cudaFree(c->d_env);
+    cudaFree(c->d_work);
+    cudaFree(c->d_counters);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RTPBR_OK;
+}
+
+int rtpbr_set_scene(RtpbrContext* c, const RtpbrObject* objects, int n)
+{
+    if (!c || !objects) return fail(RTPBR_ERR_ARG, "null argument");
+    if (n < 1 || n > RTPBR_MAX_OBJECTS) return fail(RTPBR_ERR_ARG, "object count must be in 1..RTPBR_MAX_OBJECTS");
+    for (int k = 0; k < n; ++k) {
+        if (objects[k].type < RTPBR_SHAPE_NONE || objects[k].type > RTPBR_SHAPE_BUNNY)
+            return fail(RTPBR_ERR_ARG, "bad shape type");
+        if (c->cfg.family == RTPBR_FAMILY_A && objects[k].type != RTPBR_SHAPE_BOX)
+            return fail(RTPBR_ERR_ARG, "family A (cornell_box_shortest.py) scenes are boxes only");
+    }
+    rt::fill_objects(c->P, objects, n);
+    c->have_scene = true;
+    c->blocks_per_sm = 0;  // kernel variant may change with the object count
+    return RTPBR_OK;
+}
+
+int rtpbr_set_camera(RtpbrContext* c, const RtpbrCamera* cam)
+{
+    if (!c || !cam) return fail(RTPBR_ERR_ARG, "null argument");
+    c->cam = *cam;
+    rt::fill_camera(c->P, c->cfg, c->cam);
+    c->have_camera = true;
+    return RTPBR_OK;
+}
+
+int rtpbr_set_envmap(RtpbrContext* c, const float* rgb, int w, int h)
+{
+    if (!c || !rgb || w < 1 || h < 1) return fail(RTPBR_ERR_ARG, "bad envmap");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->d_env) { cudaFree(c->d_env); c->d_env = nullptr; }
+    const size_t bytes = (size_t)w * h * 3 * sizeof(float);
+    CUDA_TRY(cudaMalloc(&c->d_env, bytes));
+    CUDA_TRY(cudaMemcpyAsync(c->d_env, rgb, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->P.env = c->d_env;
+    c->P.env_w = w;
+    c->P.env_h = h;
+    return RTPBR_OK;
+}
+
+int rtpbr_set_frame(RtpbrContext* c, int frame)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    c->P.frame = frame;
+    return RTPBR_OK;
+}
+
+int rtpbr_set_sample_base(RtpbrContext* c, uint32_t sample_base)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    c->sample_base = sample_base;
+    return RTPBR_OK;
+}
+
+int rtpbr_set_shard(RtpbrContext* c, int rank, int nranks, int band)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    if (nranks < 1 || rank < 0 || rank >= nranks || band < 1) return fail(RTPBR_ERR_ARG, "bad shard");
+    rt::fill_shard(c->P, rank, nranks, band);
+    return RTPBR_OK;
+}
+
+int rtpbr_refresh(RtpbrContext* c)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemsetAsync(c->d_image_buffer, 0, npixels(c) * sizeof(float4), c->stream));
+    return RTPBR_OK;
+}
+
+int rtpbr_pathtrace(RtpbrContext* c, int spp)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    if (spp < 1) return fail(RTPBR_ERR_ARG, "spp must be >= 1");
+    if (!c->have_scene || !c->have_camera) return fail(RTPBR_ERR_STATE, "set_scene and set_camera must precede pathtrace");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->P.spp = spp;
+    c->P.sample_base = c->sample_base;
+    const rt::KernelSelect sel = select_kernel(c);
+    if (c->kernel_events_used == c->kernel_events.size()) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreate(&a));
+        CUDA_TRY(cudaEventCreate(&b));
+        c->kernel_events.emplace_back(a, b);
+    }
+    auto& ev = c->kernel_events[c->kernel_events_used];
+    if (c->P.total_work == 0) {  // this rank owns no columns
+        c->sample_base += (uint32_t)spp;
+        return RTPBR_OK;
+    }
+    if (c->cfg.kernel == RTPBR_KERNEL_SIMPLE) {
+        CUDA_TRY(cudaEventRecord(ev.first, c->stream));
+        CUDA_TRY(rt::launch_pathtrace_simple(sel, c->P, c->stream));
+        CUDA_TRY(cudaEventRecord(ev.second, c->stream));
+    } else {
+        if (c->blocks_per_sm == 0) {
+            CUDA_TRY(rt::persistent_occupancy(sel, &c->blocks_per_sm));
+            if (c->blocks_per_sm < 1) return fail(RTPBR_ERR_CUDA, "persistent kernel does not fit on an SM");
+        }
+        int grid = c->sm_count * c->blocks_per_sm;
+        const long long need = ((long long)c->P.total_work + rt::kPersistentBlock - 1) / rt::kPersistentBlock;
+        if ((long long)grid > need) grid = (int)need;
+        CUDA_TRY(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->stream));
+        CUDA_TRY(cudaEventRecord(ev.first, c->stream));
+        CUDA_TRY(rt::launch_pathtrace_persistent(sel, c->P, grid, c->stream));
+        CUDA_TRY(cudaEventRecord(ev.second, c->stream));
+    }
+    c->kernel_events_used++;
+    c->launches++;
+    c->sample_base += (uint32_t)spp;
+    return RTPBR_OK;
+}
+
+int rtpbr_post_process(RtpbrContext* c, int mode, float exposure, float gamma)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    if (mode < 0 || mode > 3 || !(gamma > 0.f)) return fail(RTPBR_ERR_ARG, "bad tonemap arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(rt::launch_post_process(c->d_image_buffer, c->d_image_pixels, (int)npixels(c), mode, exposure,
+                                     (float)(1.0 / (double)gamma), c->stream));
+    return RTPBR_OK;
+}
+
+static int buffer_of(RtpbrContext* c, int which, void** ptr, size_t* bytes)
+{
+    switch (which) {
+    case RTPBR_BUF_IMAGE_BUFFER: *ptr = c->d_image_buffer; *bytes = npixels(c) * sizeof(float4); return RTPBR_OK;
+    case RTPBR_BUF_IMAGE_PIXELS: *ptr = c->d_image_pixels; *bytes = npixels(c) * 3 * sizeof(float); return RTPBR_OK;
+    default: return fail(RTPBR_ERR_ARG, "unknown buffer");
+    }
+}
+
+int rtpbr_download(RtpbrContext* c, int which, void* host, size_t bytes)
+{
+    if (!c || !host) return fail(RTPBR_ERR_ARG, "null argument");
+    void* d; size_t n;
+    int rc = buffer_of(c, which, &d, &n);
+    if (rc != RTPBR_OK) return rc;
+    if (bytes != n) return fail(RTPBR_ERR_ARG, "size mismatch: expected " + std::to_string(n) + " bytes");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(host, d, n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RTPBR_OK;
+}
+
+int rtpbr_upload(RtpbrContext* c, int which, const void* host, size_t bytes)
+{
+    if (!c || !host) return fail(RTPBR_ERR_ARG, "null argument");
+    void* d; size_t n;
+    int rc = buffer_of(c, which, &d, &n);
+    if (rc != RTPBR_OK) return rc;
+    if (bytes != n) return fail(RTPBR_ERR_ARG, "size mismatch: expected " + std::to_string(n) + " bytes");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(d, host, n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RTPBR_OK;
+}
+
+int rtpbr_sync(RtpbrContext* c)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RTPBR_OK;
+}
+
+int rtpbr_timer_start(RtpbrContext* c)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->ev_start, c->stream));
+    return RTPBR_OK;
+}
+
+int rtpbr_timer_stop(RtpbrContext* c, float* elapsed_ms)
+{
+    if (!c || !elapsed_ms) return fail(RTPBR_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->ev_stop, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev_stop));
+    CUDA_TRY(cudaEventElapsedTime(elapsed_ms, c->ev_start, c->ev_stop));
+    return RTPBR_OK;
+}
+
+int rtpbr_kernel_time(RtpbrContext* c, float* kernel_ms, int* launches)
+{
+    if (!c || !kernel_ms) return fail(RTPBR_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float total = 0.f;
+    for (size_t k = 0; k < c->kernel_events_used; ++k) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->kernel_events[k].first, c->kernel_events[k].second));
+        total += ms;
+    }
+    *kernel_ms = total;
+    if (launches) *launches = (int)c->kernel_events_used;
+    c->kernel_events_used = 0;
+    return RTPBR_OK;
+}
+
+int rtpbr_get_counters(RtpbrContext* c, uint64_t out[RTPBR_CNT_COUNT])
+{
+    if (!c || !out) return fail(RTPBR_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    unsigned long long h[RTPBR_CNT_COUNT];
+    CUDA_TRY(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < RTPBR_CNT_COUNT; ++k) out[k] = h[k];
+    out[RTPBR_CNT_LAUNCHES] = c->launches;
+    return RTPBR_OK;
+}
+
+int rtpbr_device_info(RtpbrContext* c, int* sm_count, int* cc_major, int* cc_minor, int* blocks_per_sm)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (blocks_per_sm) *blocks_per_sm = c->blocks_per_sm;
+    return RTPBR_OK;
+}
+
+int rtpbr_device_ptr(RtpbrContext* c, int which, uint64_t* ptr)
+{
+    if (!c || !ptr) return fail(RTPBR_ERR_ARG, "null argument");
+    void* d; size_t n;
+    int rc = buffer_of(c, which, &d, &n);
+    if (rc != RTPBR_OK) return rc;
+    *ptr = (uint64_t)(uintptr_t)d;
+    return RTPBR_OK;
+}
+
+// ------------------------------------------------------------------------------ NCCL
+int rtpbr_nccl_unique_id(void* id128)
+{
+    if (!id128) return fail(RTPBR_ERR_ARG, "null argument");
+    std::string why;
+    if (!load_nccl(why)) return fail(RTPBR_ERR_NCCL, why);
+    int r = g_nccl.GetUniqueId(id128);
+    if (r != 0) return fail(RTPBR_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+    return RTPBR_OK;
+}
+
+int rtpbr_nccl_init(RtpbrContext* c, const void* id128, int rank, int nranks)
+{
+    if (!c || !id128) return fail(RTPBR_ERR_ARG, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(RTPBR_ERR_ARG, "bad rank");
+    std::string why;
+    if (!load_nccl(why)) return fail(RTPBR_ERR_NCCL, why);
+    CUDA_TRY(cudaSetDevice(c->device));
+    UniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    int r = g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank);
+    if (r != 0) return fail(RTPBR_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    c->nccl_rank = rank;
+    c->nccl_nranks = nranks;
+    return RTPBR_OK;
+}
+
+// Sum of the per-rank accumulation buffers.  Every pixel is non-zero on exactly one rank
+// (the others hold +0.0f), so the fp32 sum is exact and equals the single-GPU buffer bit for bit.
+int rtpbr_reduce_tiles(RtpbrContext* c, int root)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    if (!c->nccl_comm) {
+        if (c->nccl_nranks == 1) return RTPBR_OK;
+        return fail(RTPBR_ERR_STATE, "rtpbr_nccl_init has not been called");
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t count = npixels(c) * 4;
+    int r;
+    if (root < 0)
+        r = g_nccl.AllReduce(c->d_image_buffer, c->d_image_buffer, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->nccl_comm,
+                             c->stream);
+    else
+        r = g_nccl.Reduce(c->d_image_buffer, c->d_image_buffer, count, 7, 0, root, c->nccl_comm, c->stream);
+    if (r != 0) return fail(RTPBR_ERR_NCCL, std::string("nccl reduce: ") + g_nccl.GetErrorString(r));
+    return RTPBR_OK;
+}
+
+}  // extern "C"

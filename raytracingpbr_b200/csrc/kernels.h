@@ -1,0 +1,25 @@
+// kernels.h -- host-callable launchers of kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rt_params.h"
+
+namespace rt {
+
+constexpr int kPersistentBlock = 256;      // 8 warps per CTA
+constexpr int kPersistentMinBlocks = 4;    // <= 64 registers/thread -> 32 warps per SM
+constexpr int kSimpleBlock = 128;
+
+struct KernelSelect {
+    int family;
+    int nobj;
+    bool count;
+};
+
+cudaError_t launch_pathtrace_persistent(const KernelSelect& sel, const KParams& P, int grid, cudaStream_t stream);
+cudaError_t launch_pathtrace_simple(const KernelSelect& sel, const KParams& P, cudaStream_t stream);
+cudaError_t persistent_occupancy(const KernelSelect& sel, int* blocks_per_sm);
+cudaError_t launch_post_process(const float4* image_buffer, float* image_pixels, int n, int mode, float exposure,
+                                float inv_gamma, cudaStream_t stream);
+
+}  // namespace rt

@@ -1,0 +1,74 @@
+// rt_params.h -- kernel parameter block (lives in the constant bank via __grid_constant__).
+#pragma once
+#include <cstdint>
+#include <vector_types.h>
+
+namespace rt {
+
+constexpr int kMaxObjects = 16;
+
+// Hot geometry of one SDF object: 16 words.  `m` is Transform.matrix (src/dataclass.py:28),
+// derived on the host by rtpbr_set_scene.
+struct DevGeom {
+    float px, py, pz;
+    float m[9];
+    float sx, sy, sz;
+    int32_t type;
+};
+
+// src/dataclass.py:13-20 Material: 12 words.
+struct DevMaterial {
+    float albedo[3];
+    float emission[3];
+    float roughness, metallic, transmission, ior;
+    float pad0, pad1;
+};
+
+struct DevCamera {
+    float origin[3];      // lookfrom
+    float llc[3];         // lower_left_corner
+    float horizontal[3];
+    float vertical[3];
+    float x[3], y[3];     // lens basis
+    float lens_radius;    // aperture * 0.5
+    float inv_w, inv_h;   // SCREEN_PIXEL_SIZE (families B/C: coord * SCREEN_PIXEL_SIZE)
+    float fw, fh;         // float(W), float(H) (family A: coord / vec2(resolution))
+};
+
+struct KParams {
+    int32_t width, height;
+    int32_t spp;
+    uint32_t sample_base;
+    uint32_t seed;
+    int32_t max_bounces, max_steps;
+    float t_start, hit_eps, t_far;
+    float relax_w0, relax_w_reset;
+    int32_t relax_guard, relax_reset;
+    float normal_h, box_round;
+    float visibility_min, visibility_max;
+    int32_t f0_variant;
+    int32_t sky;
+    float sky_scale;
+    float min_dis, pixel_radius, quality_per_sample;
+    int32_t black_background;
+    int32_t frame;
+    // shard: this context renders global columns i with (i / band) % nranks == rank
+    int32_t rank, nranks, band;
+    int32_t local_cols;      // number of columns owned by this rank
+    uint32_t total_work;     // work items (pixels incl. tile padding) on this rank
+    int32_t tiles_per_col;   // ceil(H / 8)
+    int32_t nobj;
+    int32_t resolve_q;       // resolve round when pending * 32 >= live * resolve_q
+    DevCamera cam;
+    DevGeom geom[kMaxObjects];
+    DevMaterial mat[kMaxObjects];
+    // device pointers
+    float4* image_buffer;           // (W,H) vec4, j fastest
+    const float* rr_prob;           // [max_bounces] Russian-roulette table
+    const float* env;               // (env_w, env_h, 3) or nullptr
+    int32_t env_w, env_h;
+    unsigned int* work_counter;     // persistent-kernel work queue head
+    unsigned long long* counters;   // RTPBR_CNT_* (count_work builds)
+};
+
+}  // namespace rt

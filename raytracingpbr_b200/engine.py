@@ -1,0 +1,88 @@
+"""PathTracer: the host-side object a user drives (one GPU).  Mirrors the call sequence of the
+reference's frame loops -- refresh() / pathtrace() x N / post_process() (src/renderer.py:25-32,
+bunny_sdf_glass.py:437-451) -- over the C-ABI in include/rtpbr.h."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as N
+from .dataclass import Camera, SDFObject
+
+
+class Field:
+    """Read-only view with the `.to_numpy()` / `.shape` surface of a Taichi field
+    (src/fileds.py:7-13): dense (W, H, C) float32, j fastest, origin bottom-left."""
+
+    def __init__(self, ctx: N.Context, which: int, channels: int):
+        self._ctx, self._which, self._channels = ctx, which, channels
+
+    @property
+    def shape(self):
+        return (self._ctx.width, self._ctx.height)
+
+    def to_numpy(self) -> np.ndarray:
+        return self._ctx.download(self._which)
+
+    def from_numpy(self, arr: np.ndarray) -> None:
+        self._ctx.upload(self._which, arr)
+
+
+class PathTracer:
+    def __init__(self, config: N.RtpbrConfig, objects, camera: Camera, tonemap: dict | None = None, device: int = 0):
+        self.config = config
+        self.ctx = N.Context(config, device)
+        self.tonemap = tonemap or dict(mode=2, exposure=1.0, gamma=2.2)
+        self.image_buffer = Field(self.ctx, N.BUF_IMAGE_BUFFER, 4)     # src/fileds.py:8
+        self.image_pixels = Field(self.ctx, N.BUF_IMAGE_PIXELS, 3)     # src/fileds.py:9
+        self.set_scene(objects)
+        self.set_camera(camera)
+
+    # scene / camera ----------------------------------------------------------------------
+    def set_scene(self, objects) -> None:
+        self.objects = list(objects)
+        self.ctx.set_scene([o.to_native() if isinstance(o, SDFObject) else o for o in self.objects])
+
+    def set_camera(self, camera: Camera) -> None:
+        self.camera = camera
+        self.ctx.set_camera(camera.to_native() if isinstance(camera, Camera) else camera)
+
+    # frame loop --------------------------------------------------------------------------
+    def refresh(self) -> None:
+        """kernel refresh(), src/renderer.py:12-22."""
+        self.ctx.refresh()
+
+    def pathtrace(self, spp: int = 1) -> None:
+        """`spp` x kernel pathtrace()/sample()/render() launches of the reference, in one launch."""
+        self.ctx.pathtrace(spp)
+
+    def post_process(self) -> None:
+        """kernel post_process(), src/postprocessor.py:24-38 (variant chosen by the preset)."""
+        self.ctx.post_process(self.tonemap["mode"], self.tonemap["exposure"], self.tonemap["gamma"])
+
+    def render(self, spp: int = 1, refreshing: bool = False) -> None:
+        """render(refreshing), src/renderer.py:25-32."""
+        if refreshing:
+            self.refresh()
+        self.pathtrace(spp)
+        self.post_process()
+
+    def sync(self) -> None:
+        self.ctx.sync()
+
+    def close(self) -> None:
+        self.ctx.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def imwrite(pixels: np.ndarray, path: str) -> None:
+    """ti.tools.imwrite(field, path) stand-in (src/main.py:55): (W,H,3) f32 in [0,1], origin
+    bottom-left -> PNG with origin top-left."""
+    from PIL import Image
+    a = np.clip(np.asarray(pixels), 0.0, 1.0)
+    img = (a.transpose(1, 0, 2)[::-1] * 255.0).astype(np.uint8)
+    Image.fromarray(img).save(path)

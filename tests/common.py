@@ -1,0 +1,98 @@
+"""Shared helpers for the test-suite: product structs -> oracle structs, host-check loader."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import pyoracle as po  # noqa: E402  (test infrastructure)
+from raytracingpbr_b200 import _native as N  # noqa: E402
+from raytracingpbr_b200.dataclass import Camera, SDFObject  # noqa: E402
+
+
+def to_oracle(cfg: N.RtpbrConfig, camera: Camera, objects):
+    """Translate the product's (config, camera, objects) into the oracle's own structs."""
+    oc = po.OrcConfig()
+    for name, _ in N.RtpbrConfig._fields_:
+        if name in ("kernel", "count_work"):
+            continue
+        setattr(oc, name, getattr(cfg, name))
+    nc = camera.to_native() if isinstance(camera, Camera) else camera
+    oc.lookfrom[:] = list(nc.lookfrom)
+    oc.lookat[:] = list(nc.lookat)
+    oc.vup[:] = list(nc.vup)
+    oc.vfov, oc.aspect, oc.aperture, oc.focus = nc.vfov, nc.aspect, nc.aperture, nc.focus
+    oc.frame = 0
+    oobjs = []
+    for o in objects:
+        n = o.to_native() if isinstance(o, SDFObject) else o
+        oo = po.OrcObject()
+        for name, _ in po.OrcObject._fields_:
+            v = getattr(n, name)
+            if hasattr(v, "__len__"):
+                getattr(oo, name)[:] = list(v)
+            else:
+                setattr(oo, name, v)
+        oobjs.append(oo)
+    return oc, po.objects_array(oobjs)
+
+
+_HC = None
+_HC_DIR = os.path.join(ROOT, "tests", "native")
+
+
+def hostcheck() -> C.CDLL:
+    """Build (if stale) and load tests/native/libhostcheck.so: the product's
+    __host__ __device__ integrator code compiled for the CPU (test harness only)."""
+    global _HC
+    if _HC is not None:
+        return _HC
+    so = os.path.join(_HC_DIR, "libhostcheck.so")
+    src = os.path.join(_HC_DIR, "hostcheck.cu")
+    csrc = os.path.join(ROOT, "raytracingpbr_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call([
+            "nvcc", "-O2", "-std=c++17", "-shared", "-Wno-deprecated-gpu-targets", "-Xcompiler",
+            "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma,-fopenmp,-fvisibility=hidden", "-o", so, src, "-lgomp"],
+            stderr=subprocess.DEVNULL)
+    L = C.CDLL(so)
+    L.hostcheck_pathtrace.restype = C.c_int
+    L.hostcheck_pathtrace.argtypes = [C.POINTER(N.RtpbrConfig), C.POINTER(N.RtpbrCamera), C.POINTER(N.RtpbrObject), C.c_int,
+                                      C.POINTER(C.c_float), C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    L.hostcheck_sincos.restype = None
+    L.hostcheck_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.hostcheck_atan2.restype = C.c_float
+    L.hostcheck_atan2.argtypes = [C.c_float, C.c_float]
+    L.hostcheck_asin.restype = C.c_float
+    L.hostcheck_asin.argtypes = [C.c_float]
+    L.hostcheck_euler.restype = None
+    L.hostcheck_euler.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    _HC = L
+    return L
+
+
+def hostcheck_pathtrace(cfg, camera, objects, spp, sample_base=0, image=None, rank=0, nranks=1, band=32):
+    L = hostcheck()
+    nobjs = [o.to_native() if isinstance(o, SDFObject) else o for o in objects]
+    arr = (N.RtpbrObject * len(nobjs))(*nobjs)
+    cam = camera.to_native() if isinstance(camera, Camera) else camera
+    if image is None:
+        image = np.zeros((cfg.width, cfg.height, 4), dtype=np.float32)
+    rc = L.hostcheck_pathtrace(C.byref(cfg), C.byref(cam), arr, len(nobjs), image.ctypes.data_as(C.POINTER(C.c_float)),
+                               spp, sample_base, rank, nranks, band)
+    assert rc == 0, rc
+    return image
+
+
+def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
