@@ -163,6 +163,8 @@ RTPBR_API int rtpbr_download(RtpbrContext* ctx, int which, void* host, size_t by
 /* resume from a saved accumulation buffer (reference has no checkpointing) */
 RTPBR_API int rtpbr_upload(RtpbrContext* ctx, int which, const void* host, size_t bytes);
 RTPBR_API int rtpbr_sync(RtpbrContext* ctx);
+/* benchmark hygiene: evict L2 by writing a 256 MiB scratch buffer on the launch stream */
+RTPBR_API int rtpbr_flush_l2(RtpbrContext* ctx);
 
 /* CUDA-event timing on the context's launch stream (bench.py) */
 RTPBR_API int rtpbr_timer_start(RtpbrContext* ctx);

@@ -29,7 +29,7 @@ CNT_NAMES = ("scene_evals", "rays", "normals", "samples", "march_iters", "march_
 EXPORTS = (
     "rtpbr_create", "rtpbr_destroy", "rtpbr_set_scene", "rtpbr_set_camera", "rtpbr_set_envmap", "rtpbr_set_frame",
     "rtpbr_set_sample_base", "rtpbr_set_shard", "rtpbr_refresh", "rtpbr_pathtrace", "rtpbr_post_process",
-    "rtpbr_download", "rtpbr_upload", "rtpbr_sync", "rtpbr_timer_start", "rtpbr_timer_stop", "rtpbr_kernel_time",
+    "rtpbr_download", "rtpbr_upload", "rtpbr_sync", "rtpbr_flush_l2", "rtpbr_timer_start", "rtpbr_timer_stop", "rtpbr_kernel_time",
     "rtpbr_get_counters", "rtpbr_device_info", "rtpbr_nccl_unique_id", "rtpbr_nccl_init", "rtpbr_reduce_tiles",
     "rtpbr_device_ptr", "rtpbr_last_error", "rtpbr_version", "rtpbr_sizeof_config", "rtpbr_sizeof_object",
     "rtpbr_sizeof_camera",
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
         "rtpbr_download": [vp, C.c_int, vp, C.c_size_t],
         "rtpbr_upload": [vp, C.c_int, vp, C.c_size_t],
         "rtpbr_sync": [vp],
+        "rtpbr_flush_l2": [vp],
         "rtpbr_timer_start": [vp],
         "rtpbr_timer_stop": [vp, C.POINTER(C.c_float)],
         "rtpbr_kernel_time": [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
@@ -220,6 +221,9 @@ class Context:
 
     def sync(self) -> None:
         check(self._L.rtpbr_sync(self._h))
+
+    def flush_l2(self) -> None:
+        check(self._L.rtpbr_flush_l2(self._h))
 
     # -- data -------------------------------------------------------------------------
     def download(self, which: int = BUF_IMAGE_BUFFER, out: np.ndarray | None = None) -> np.ndarray:

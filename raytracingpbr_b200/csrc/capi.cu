@@ -85,6 +85,7 @@ struct RtpbrContext {
     float* d_env = nullptr;
     unsigned int* d_work = nullptr;
     unsigned long long* d_counters = nullptr;
+    void* d_flush = nullptr;
     bool have_scene = false, have_camera = false;
     uint32_t sample_base = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0, blocks_per_sm = 0;
@@ -209,6 +210,7 @@ int rtpbr_destroy(RtpbrContext* c)
     cudaFree(c->d_env);
     cudaFree(c->d_work);
     cudaFree(c->d_counters);
+    cudaFree(c->d_flush);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RTPBR_OK;
@@ -378,6 +380,16 @@ int rtpbr_sync(RtpbrContext* c)
     if (!c) return fail(RTPBR_ERR_ARG, "null context");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RTPBR_OK;
+}
+
+int rtpbr_flush_l2(RtpbrContext* c)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)256 << 20;   // > 126 MB L2
+    if (!c->d_flush) CUDA_TRY(cudaMalloc(&c->d_flush, bytes));
+    CUDA_TRY(cudaMemsetAsync(c->d_flush, 0, bytes, c->stream));
     return RTPBR_OK;
 }
 

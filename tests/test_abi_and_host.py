@@ -1,0 +1,120 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/rtpbr.h declares
+(no compute calls without a GPU), the product's host-side setup and its __host__ __device__
+integrator code (compiled for the CPU by tests/native/hostcheck.cu) agree bit for bit with the
+independent C oracle, and the product fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import common
+from common import po
+from conftest import HAVE_GPU
+from raytracingpbr_b200 import RtpbrError, _native as N, scenes
+from raytracingpbr_b200.dataclass import Camera, Material, SDFObject, Transform
+from raytracingpbr_b200.tmath import vec3
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(common.ROOT, "include", "rtpbr.h")).read()
+    declared = set(re.findall(r"RTPBR_API\s+[\w\s\*]+?\b(rtpbr_\w+)\s*\(", hdr))
+    assert declared == set(N.EXPORTS), declared ^ set(N.EXPORTS)
+    L = N.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.rtpbr_version() == 1
+
+
+def test_struct_layouts_match_header():
+    L = N.lib()
+    assert L.rtpbr_sizeof_config() == C.sizeof(N.RtpbrConfig)
+    assert L.rtpbr_sizeof_object() == C.sizeof(N.RtpbrObject) == 80
+    assert L.rtpbr_sizeof_camera() == C.sizeof(N.RtpbrCamera) == 52
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_fails_loudly():
+    cfg = scenes.cornell_box_shortest(8, 8)[0]
+    with pytest.raises(RtpbrError) as e:
+        N.Context(cfg)
+    assert e.value.code == N.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_argument_validation_without_gpu():
+    L = N.lib()
+    h = C.c_void_p()
+    assert L.rtpbr_create(None, 0, C.byref(h)) == N.ERR_ARG
+    bad = scenes.cornell_box_shortest(8, 8)[0]
+    bad.max_bounces = 0
+    assert L.rtpbr_create(C.byref(bad), 0, C.byref(h)) == N.ERR_ARG
+    assert b"max_bounces" in L.rtpbr_last_error()
+    assert L.rtpbr_pathtrace(None, 1) == N.ERR_ARG
+    assert L.rtpbr_destroy(None) == 0
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(common.ROOT, "raytracingpbr_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                for needle in ("pyoracle", "liboracle", "import oracle", "from oracle", "oracle.c", "oracle/"):
+                    assert needle not in txt, (f, needle)
+
+
+def test_dataclass_surface_positional_like_reference():
+    # src/scene.py:13-14 construction style
+    o = SDFObject(2, Transform(vec3(0, 0, -1), vec3(0), vec3(1, 1, 0.2)), Material(vec3(1, 1, 1) * 0.6, vec3(1), 1.0, 1.0, 0, 1.100))
+    n = o.to_native()
+    assert n.type == 2 and list(n.scale) == [1.0, 1.0, np.float32(0.2)] and list(n.albedo) == [np.float32(0.6)] * 3
+    assert n.ior == np.float32(1.1) and n.metallic == 1.0
+    c = Camera(vec3(0, 0, 3.5), vec3(0, 0, -1), vec3(0, 1, 0), 35.0, 1.0, 0.0, 1.0).to_native()
+    assert list(c.lookfrom) == [0, 0, 3.5] and c.vfov == 35.0
+
+
+def test_host_transcendentals_match_oracle_bitwise():
+    H, L = common.hostcheck(), po.lib()
+    s1, c1, s2, c2 = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    for x in np.linspace(-40, 40, 4001).astype(np.float32):
+        H.hostcheck_sincos(float(x), C.byref(s1), C.byref(c1))
+        L.orc_sincosf(float(x), C.byref(s2), C.byref(c2))
+        assert s1.value == s2.value and c1.value == c2.value
+    rng = np.random.default_rng(3)
+    for y, x in rng.normal(size=(2000, 2)).astype(np.float32):
+        assert H.hostcheck_atan2(float(y), float(x)) == L.orc_atan2f(float(y), float(x))
+    for x in np.linspace(-1.1, 1.1, 1001).astype(np.float32):
+        assert H.hostcheck_asin(float(x)) == L.orc_asinf(float(x))
+
+
+def test_host_euler_matrix_matches_oracle_bitwise():
+    H, L = common.hostcheck(), po.lib()
+    a, b = np.zeros(9, np.float32), np.zeros(9, np.float32)
+    f32p = lambda v: v.ctypes.data_as(C.POINTER(C.c_float))
+    for rot in ([0, 0, 0], [90, 0, 0], [0, 112, 0], [0, -197, 0], [13.5, -77.25, 211.0]):
+        r = np.array(rot, np.float32)
+        H.hostcheck_euler(f32p(r), f32p(a))
+        L.orc_angle_deg(f32p(r), f32p(b))
+        assert np.array_equal(a, b), rot
+
+
+@pytest.mark.parametrize("w,h,spp,b,seed", [(48, 40, 2, 4, 0), (33, 17, 3, 8, 5), (5, 3, 4, 16, 9)])
+def test_product_integrator_on_host_matches_oracle_bitwise(w, h, spp, b, seed):
+    cfg, objs, cam, _ = scenes.cornell_box_shortest(w, h, max_bounces=b, seed=seed)
+    got = common.hostcheck_pathtrace(cfg, cam, objs, spp)
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    want = po.pathtrace(oc, oo, spp)
+    assert np.array_equal(got, want)
+
+
+def test_product_shard_mapping_on_host():
+    cfg, objs, cam, _ = scenes.cornell_box_shortest(70, 20, max_bounces=4, seed=1)
+    full = common.hostcheck_pathtrace(cfg, cam, objs, 2)
+    acc = np.zeros_like(full)
+    for r in range(4):
+        part = common.hostcheck_pathtrace(cfg, cam, objs, 2, rank=r, nranks=4, band=8)
+        own = ((np.arange(70) // 8) % 4) == r
+        assert (part[~own] == 0).all() and (part[own][..., 3] == 2).all()
+        acc += part
+    assert np.array_equal(acc, full)
