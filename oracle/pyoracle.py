@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
         L.orc_angle_deg.argtypes = [f32p, f32p]
         L.orc_philox4x32_10.restype = None
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.orc_random.restype = C.c_float
+        L.orc_random.argtypes = [C.c_uint32] * 4
         L.orc_draw4.restype = None
         L.orc_draw4.argtypes = [C.c_uint32] * 5 + [f32p]
         assert L.orc_sizeof_config() == C.sizeof(OrcConfig), "OrcConfig layout mismatch"

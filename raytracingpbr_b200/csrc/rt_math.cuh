@@ -6,8 +6,9 @@
 // code with -ffp-contract=off, so the only fused operations are the explicit fmaf() calls:
 //   dot(a,b)   = fmaf(a.z,b.z, fmaf(a.y,b.y, a.x*b.x));  M@v = per-row dot
 //   length(v)  = sqrtf(dot(v,v)) (IEEE, -prec-sqrt=true);  normalize(v) = v * (1.0f/length(v))
-//   at(o,d,t)  = fmaf(t, d, o)
-//   everything else: one IEEE binary32 rounding per written operator.
+//   mix(a,b,t) = a*(1-t) + b*t;  pow(x, 5.0) = ((x*x)*(x*x))*x
+//   every operator the reference itself writes (+ - * /, e.g. origin + t * direction) is ONE
+//   IEEE binary32 rounding, left to right, never contracted.
 // sin/cos/atan2/asin are the polynomial routines below -- never libdevice/libm, which differ
 // bitwise between host and device.
 #pragma once
@@ -40,7 +41,7 @@ RT_HD vec3 cross(vec3 a, vec3 b)
 {
     return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-RT_HD vec3 at(vec3 o, vec3 d, float t) { return V3(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)); }
+RT_HD vec3 at(vec3 o, vec3 d, float t) { return o + d * t; }  // ray.origin + t * ray.direction
 RT_HD vec3 mat_mul(const float* m, vec3 v)
 {
     return V3(fmaf(m[2], v.z, fmaf(m[1], v.y, m[0] * v.x)), fmaf(m[5], v.z, fmaf(m[4], v.y, m[3] * v.x)),
@@ -141,16 +142,33 @@ RT_HD float u01(uint32_t u) { return (float)(u >> 8) * 0x1p-24f; }  // Taichi u3
 
 constexpr uint32_t kPhiloxKey1 = 0x52545042u;  // "RTPB"
 
-struct rand4 { float r0, r1, r2, r3; };
-// Draw block: counter = (pixel, sample, block, stream); key = (seed, kPhiloxKey1).
-//   block 0       : (jitter x, jitter y, lens r, lens angle)
-//   block 1 + i   : bounce i: (russian roulette, hemisphere z, hemisphere angle, reflect test);
-//                   stream 1 of the same block: (transmission test, -, -, -)
-RT_HD rand4 draw4(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t block, uint32_t stream)
+// RNG CONTRACT: the n-th ti.random() call (n = 0, 1, ...) a pixel makes inside kernel launch
+// number L is word (n & 3) of Philox4x32-10(counter = (pixel, L, n >> 2, 0), key = (seed,
+// "RTPB")), pixel = i * height + j.  Families A/B trace one sample per launch, so L is the
+// sample index.  Nothing else about the path structure enters the RNG, so regeneration and
+// compaction cannot change which numbers a sample sees.
+RT_HD float pick4(const uint4_rt& o, uint32_t k)
 {
-    uint4_rt o = philox4x32_10(pixel, sample, block, stream, seed, kPhiloxKey1);
-    rand4 r; r.r0 = u01(o.x); r.r1 = u01(o.y); r.r2 = u01(o.z); r.r3 = u01(o.w);
-    return r;
+    uint32_t u = k == 0u ? o.x : (k == 1u ? o.y : (k == 2u ? o.z : o.w));
+    return u01(u);
+}
+RT_HD float rng_at(uint32_t seed, uint32_t pixel, uint32_t launch, uint32_t n)
+{
+    return pick4(philox4x32_10(pixel, launch, n >> 2, 0u, seed, kPhiloxKey1), n & 3u);
+}
+// Draws n, n+1, n+2 of the stream with at most two Philox evaluations.
+RT_HD void rng_at3(uint32_t seed, uint32_t pixel, uint32_t launch, uint32_t n, float& a, float& b, float& c)
+{
+    const uint32_t blk = n >> 2, k = n & 3u;
+    uint4_rt o = philox4x32_10(pixel, launch, blk, 0u, seed, kPhiloxKey1);
+    if (k <= 1u) {
+        a = pick4(o, k); b = pick4(o, k + 1u); c = pick4(o, k + 2u);
+    } else {
+        uint4_rt q = philox4x32_10(pixel, launch, blk + 1u, 0u, seed, kPhiloxKey1);
+        a = pick4(o, k);
+        b = k == 2u ? u01(o.w) : u01(q.x);
+        c = k == 2u ? u01(q.x) : u01(q.y);
+    }
 }
 
 }  // namespace rt

@@ -9,7 +9,7 @@ constexpr int kMaxObjects = 16;
 
 // Hot geometry of one SDF object: 16 words.  `m` is Transform.matrix (src/dataclass.py:28),
 // derived on the host by rtpbr_set_scene.
-struct DevGeom {
+struct alignas(16) DevGeom {
     float px, py, pz;
     float m[9];
     float sx, sy, sz;

@@ -1,0 +1,102 @@
+"""Golden-vector tests: the oracle (CPU, always) and the CUDA path (-m gpu) against fixtures
+produced by executing the reference's own source files under tests/tools/taichi_shim
+(tests/tools/gen_golden.py).  Everything is compared BIT FOR BIT."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import common
+from common import po
+
+GOLDEN = os.path.join(common.ROOT, "tests", "golden")
+SHORTEST = sorted(glob.glob(os.path.join(GOLDEN, "shortest_*.npz")))
+
+
+def f32p(a):
+    return np.ascontiguousarray(a, dtype=np.float32).ctypes.data_as(C.POINTER(C.c_float))
+
+
+def params(g):
+    return tuple(int(g[k]) for k in ("width", "height", "bounces", "spp", "seed"))
+
+
+def test_fixtures_present():
+    assert len(SHORTEST) >= 2
+
+
+@pytest.mark.parametrize("path", SHORTEST, ids=os.path.basename)
+def test_oracle_image_buffer_matches_reference_source(path):
+    g = np.load(path)
+    W, H, B, S, seed = params(g)
+    cfg = po.cornell_shortest_config(W, H, B, seed)
+    objs = po.objects_array(po.cornell_shortest_objects())
+    assert np.array_equal(po.pathtrace(cfg, objs, 1), g["image_buffer_first"])
+    assert np.array_equal(po.pathtrace(cfg, objs, S), g["image_buffer"])
+    # as-written mode (matrices recomputed per evaluation, shortest:43) gives the same bits
+    assert np.array_equal(po.pathtrace(cfg, objs, S, hoisted=False), g["image_buffer"])
+
+
+@pytest.mark.parametrize("path", SHORTEST[:1], ids=os.path.basename)
+def test_oracle_functions_match_reference_source(path):
+    g = np.load(path)
+    W, H, B, S, seed = params(g)
+    cfg = po.cornell_shortest_config(W, H, B, seed)
+    objs = po.objects_array(po.cornell_shortest_objects())
+    L = po.lib()
+    for p, row in zip(g["sd_points"], g["sd_values"]):            # signed_distance, shortest:41-45
+        for k in range(8):
+            for hoisted in (0, 1):
+                assert np.float32(L.orc_signed_distance(C.byref(cfg), objs, 8, k, f32p(p), hoisted)) == row[k]
+    out = np.zeros(9, np.float32)
+    for r, m in zip(g["angle_deg"], g["angle_mat"]):              # angle(radians(.)), shortest:34-39
+        L.orc_angle_deg(f32p(r), f32p(out))
+        assert np.array_equal(out.reshape(3, 3), m)
+    n = np.zeros(3, np.float32)
+    for q, want in zip(g["normal_in"], g["normal_out"]):          # calc_normal, shortest:55-61
+        L.orc_calc_normal(C.byref(cfg), objs, 8, int(q[3]), f32p(q[:3]), f32p(n))
+        assert np.array_equal(n, want)
+    rec = np.zeros(7, np.float32)
+    albedo = np.array([list(o.albedo) for o in objs], np.float32)
+    for row in g["raycast"]:                                      # raycast, shortest:63-72
+        L.orc_raycast(C.byref(cfg), objs, 8, f32p(row[0:3]), f32p(row[3:6]), f32p(rec))
+        assert rec[0] == row[6] and rec[3] == row[7]
+        assert np.array_equal(rec[4:7], row[8:11])
+        if row[6]:
+            assert np.array_equal(albedo[int(rec[1])], row[11:14])
+    h = np.zeros(3, np.float32)
+    for row in g["hemi"]:                                         # hemispheric_sampling, shortest:74-79
+        L.orc_hemispheric_sampling(f32p(row[0:3]), float(row[3]), float(row[4]), f32p(h))
+        assert np.array_equal(h, row[5:8])
+
+
+@pytest.mark.parametrize("path", SHORTEST, ids=os.path.basename)
+def test_product_host_code_matches_reference_source(path):
+    # the product's __host__ __device__ integrator compiled for the CPU (tests/native/hostcheck.cu)
+    from raytracingpbr_b200 import scenes
+    g = np.load(path)
+    W, H, B, S, seed = params(g)
+    cfg, objs, cam, _ = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=seed)
+    assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, S), g["image_buffer"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", SHORTEST, ids=os.path.basename)
+def test_cuda_image_buffer_matches_reference_source(path):
+    from raytracingpbr_b200 import PathTracer, _native as N, scenes
+    g = np.load(path)
+    W, H, B, S, seed = params(g)
+    for kernel in (N.KERNEL_PERSISTENT, N.KERNEL_SIMPLE):
+        cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=seed, kernel=kernel)
+        with PathTracer(cfg, objs, cam, tm) as pt:
+            pt.refresh()
+            for _ in range(S):                      # one launch per sample, like the reference's main loop
+                pt.pathtrace(1)
+            pt.post_process()
+            buf = pt.image_buffer.to_numpy()
+            pix = pt.image_pixels.to_numpy()
+        assert np.array_equal(buf, g["image_buffer"])
+        # tone mapping uses pow(): tolerance, not bits (shortest:124-129)
+        np.testing.assert_allclose(pix, g["image_pixels"], atol=2e-5)

@@ -42,6 +42,15 @@ def test_uniform_conversion_is_taichi_rule():
     assert all(0.0 <= v < 1.0 for v in out)
 
 
+def test_sequential_stream_contract():
+    # n-th ti.random() of (pixel, launch) = word n & 3 of Philox(counter = (pixel, launch, n >> 2, 0))
+    L = po.lib()
+    raw = (C.c_uint32 * 4)()
+    for n in range(11):
+        L.orc_philox4x32_10((C.c_uint32 * 4)(77, 5, n >> 2, 0), (C.c_uint32 * 2)(9, 0x52545042), raw)
+        assert L.orc_random(9, 77, 5, n) == np.float32((raw[n & 3] >> 8) * 2.0 ** -24)
+
+
 def test_sincos_accuracy():
     L = po.lib()
     s, c = C.c_float(), C.c_float()
