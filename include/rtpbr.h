@@ -112,6 +112,11 @@ typedef struct RtpbrConfig {
     float pixel_radius;           /* PIXEL_RADIUS, src/config.py:20 */
     float quality_per_sample;     /* QUALITY_PER_SAMPLE, src/config.py:11 */
     int32_t black_background;     /* BLACK_BACKGROUND, src/config.py:13 */
+    int32_t nearest_seed;         /* 0: first object seeds the minimum (shortest:48, cornell_box.py:198);
+                                     1: MAX_DIS seeds it (src/scene.py:46, tokyo_ibl.py:222) */
+    int32_t normal_mode;          /* 0: world-space tetrahedron offsets (shortest:55-61);
+                                     1: object-space, one transform (src/sdf.py:77-87) */
+    int32_t samples_per_pixel;    /* SAMPLES_PER_PIXEL per launch, src/config.py:10 (family C) */
     int32_t kernel;               /* RTPBR_KERNEL_* */
     int32_t count_work;           /* 1: count scene evals / rays / lane occupancy (slower) */
 } RtpbrConfig;

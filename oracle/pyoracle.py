@@ -55,6 +55,7 @@ class OrcConfig(C.Structure):
         ("frame", C.c_int32),
         ("min_dis", C.c_float), ("pixel_radius", C.c_float), ("quality_per_sample", C.c_float),
         ("black_background", C.c_int32),
+        ("nearest_seed", C.c_int32), ("normal_mode", C.c_int32), ("samples_per_pixel", C.c_int32),
     ]
 
 
@@ -82,6 +83,21 @@ def lib() -> C.CDLL:
         L.orc_pathtrace.restype = C.c_int
         L.orc_pathtrace.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, C.c_int, C.c_uint32,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OrcCounters)]
+        L.orc_pathtrace_ex.restype = C.c_int
+        L.orc_pathtrace_ex.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, f32p, f32p, C.c_int, C.c_int,
+                                       C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OrcCounters)]
+        L.orc_signed_distance_g.restype = C.c_float
+        L.orc_signed_distance_g.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, C.c_int, f32p]
+        L.orc_nearest_g.restype = C.c_int
+        L.orc_nearest_g.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, f32p]
+        L.orc_calc_normal_g.restype = None
+        L.orc_calc_normal_g.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, C.c_int, f32p, f32p]
+        L.orc_raycast_g.restype = None
+        L.orc_raycast_g.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, f32p, f32p]
+        L.orc_sd_bunny.restype = C.c_float
+        L.orc_sd_bunny.argtypes = [f32p]
+        L.orc_sky_envmap.restype = None
+        L.orc_sky_envmap.argtypes = [f32p, C.c_int, C.c_int, f32p, f32p]
         L.orc_sd_box.restype = C.c_float
         L.orc_sd_box.argtypes = [f32p, f32p, C.c_float]
         L.orc_signed_distance.restype = C.c_float
@@ -189,23 +205,34 @@ def cornell_shortest_config(width=512, height=512, max_bounces=3, seed=0) -> Orc
     c.seed = seed
     c.frame = 0
     c.min_dis, c.pixel_radius, c.quality_per_sample, c.black_background = 0.0, 0.0, 0.8, 0
+    c.nearest_seed, c.normal_mode, c.samples_per_pixel = 0, 0, 1
     return c
 
 
 def pathtrace(cfg: OrcConfig, objs, spp: int, sample_base: int = 0, image_buffer: np.ndarray | None = None,
-              i0: int = 0, i1: int | None = None, hoisted: bool = True, nthreads: int = 0, counters: bool = False):
-    """Accumulate `spp` samples per pixel; returns the (W,H,4) f32 buffer (and counters)."""
+              i0: int = 0, i1: int | None = None, hoisted: bool = True, nthreads: int = 0, counters: bool = False,
+              ray_buffer: np.ndarray | None = None, env: np.ndarray | None = None):
+    """Accumulate `spp` samples per pixel (families A/B) or run `spp` launches of kernel
+    pathtrace() (family C, state in `ray_buffer` (W,H,10) f32 with depth as raw int32 bits);
+    returns the (W,H,4) f32 buffer (and counters).  `env` is the processed (w,h,3) f32 table."""
     L = lib()
     W, H = cfg.width, cfg.height
     if image_buffer is None:
         image_buffer = np.zeros((W, H, 4), dtype=np.float32)
     assert image_buffer.shape == (W, H, 4) and image_buffer.dtype == np.float32 and image_buffer.flags.c_contiguous
+    if cfg.family == FAMILY_C:
+        assert ray_buffer is not None and ray_buffer.shape == (W, H, 10) and ray_buffer.dtype == np.float32
+    if env is not None:
+        assert env.dtype == np.float32 and env.flags.c_contiguous and env.ndim == 3 and env.shape[2] == 3
     arr = objs if isinstance(objs, C.Array) else objects_array(objs)
     cnt = OrcCounters()
-    rc = L.orc_pathtrace(C.byref(cfg), arr, len(arr), _f32p(image_buffer), spp, sample_base, i0,
-                         W if i1 is None else i1, int(hoisted), nthreads, C.byref(cnt) if counters else None)
+    rc = L.orc_pathtrace_ex(C.byref(cfg), arr, len(arr), _f32p(image_buffer),
+                            _f32p(ray_buffer) if ray_buffer is not None else None,
+                            _f32p(env) if env is not None else None, env.shape[0] if env is not None else 0,
+                            env.shape[1] if env is not None else 0, spp, sample_base, i0,
+                            W if i1 is None else i1, int(hoisted), nthreads, C.byref(cnt) if counters else None)
     if rc != 0:
-        raise RuntimeError(f"orc_pathtrace failed: {rc}")
+        raise RuntimeError(f"orc_pathtrace_ex failed: {rc}")
     if counters:
         return image_buffer, {k: getattr(cnt, k) for k, _ in OrcCounters._fields_}
     return image_buffer

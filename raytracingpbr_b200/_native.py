@@ -71,6 +71,7 @@ class RtpbrConfig(C.Structure):
         ("seed", C.c_uint32),
         ("min_dis", C.c_float), ("pixel_radius", C.c_float), ("quality_per_sample", C.c_float),
         ("black_background", C.c_int32),
+        ("nearest_seed", C.c_int32), ("normal_mode", C.c_int32), ("samples_per_pixel", C.c_int32),
         ("kernel", C.c_int32), ("count_work", C.c_int32),
     ]
 

@@ -96,3 +96,44 @@ def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
     a = a.astype(np.float64)
     b = b.astype(np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# ------------------------------------------------------------------------------ golden fixtures
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def env_table(u8: np.ndarray, exposure: float, gamma: float) -> np.ndarray:
+    """Independent restatement (test side) of Image.__init__/process (src/ibl.py:12-23,
+    tokyo_ibl.py:40-51): (u8 / 255 * exposure) ** gamma, pow in binary64 rounded once."""
+    x = (u8.astype(np.float32) / np.float32(255)) * np.float32(exposure)
+    return np.power(x.astype(np.float64), float(np.float32(gamma))).astype(np.float32)
+
+
+def golden_case(name: str):
+    """(fixture, RtpbrConfig, objects, camera, tonemap, processed env table or None) of a golden fixture."""
+    from raytracingpbr_b200 import scenes
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    W, H, seed = int(g["width"]), int(g["height"]), int(g["seed"])
+    env = None
+    if name.startswith("shortest"):
+        cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=int(g["bounces"]), seed=seed)
+    elif name == "cornell_box":
+        cfg, objs, cam, tm = scenes.cornell_box(W, H, max_bounces=int(g["bounces"]), seed=seed)
+    elif name == "cornell_v3":
+        cfg, objs, cam, tm = scenes.cornell_box_v3(W, H, max_bounces=int(g["bounces"]), seed=seed)
+    elif name == "tokyo_ibl":
+        cfg, objs, cam, tm = scenes.tokyo_ibl(W, H, seed=seed)
+        env = env_table(g["env_u8"], 1.8, 2.2)                      # tokyo_ibl.py:60
+    elif name == "scene_demo":
+        cfg, objs, cam, tm = scenes.scene_demo(W, H, seed=seed)
+    elif name == "bunny_glass":
+        cfg, objs, cam, tm = scenes.bunny_glass(W, H, max_bounces=int(g["bounces"]), seed=seed, frame=int(g["frame"]))
+        env = env_table(g["env_u8"], 1.8, 2.2)                      # bunny_sdf_glass.py:279-280, applied per texel
+    elif name == "src_scene":
+        cfg, objs, cam, tm = scenes.src_scene(W, H, seed=seed)
+        env = env_table(g["env_u8"], 1.4, 2.2)                      # src/ibl.py:33
+    else:
+        raise KeyError(name)
+    if "lookfrom" in g:
+        cam.lookfrom, cam.lookat = g["lookfrom"], g["lookat"]
+    return g, cfg, objs, cam, tm, env

@@ -82,6 +82,73 @@ def test_product_host_code_matches_reference_source(path):
     assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, S), g["image_buffer"])
 
 
+FAMILY_B = ["cornell_box", "cornell_v3", "tokyo_ibl", "scene_demo", "bunny_glass"]
+
+
+def oracle_of(name):
+    g, cfg, objs, cam, tm, env = common.golden_case(name)
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    if "frame" in g:
+        oc.frame = int(g["frame"])
+    return g, oc, oo, env
+
+
+@pytest.mark.parametrize("name", FAMILY_B)
+def test_oracle_family_b_image_buffer_matches_reference_source(name):
+    g, oc, oo, env = oracle_of(name)
+    assert np.array_equal(po.pathtrace(oc, oo, 1, env=env), g["image_buffer_first"])
+    assert np.array_equal(po.pathtrace(oc, oo, int(g["spp"]), env=env), g["image_buffer"])
+
+
+@pytest.mark.parametrize("name", FAMILY_B + ["src_scene"])
+def test_oracle_family_bc_functions_match_reference_source(name):
+    g, oc, oo, env = oracle_of(name)
+    L, n = po.lib(), len(oo)
+    if "sd_values" in g:                                       # signed_distance of every object
+        for p, row in zip(g["sd_points"], g["sd_values"]):
+            for k in range(len(row)):
+                assert np.float32(L.orc_signed_distance_g(C.byref(oc), oo, n, k, f32p(p))) == row[k]
+    if "nearest" in g:                                         # nearest / nearest_object
+        d = C.c_float()
+        for p, row in zip(g["sd_points"], g["nearest"]):
+            assert L.orc_nearest_g(C.byref(oc), oo, n, f32p(p), C.byref(d)) == int(row[0])
+            assert np.float32(d.value) == row[1]
+    if "normal_out" in g:                                      # calc_normal
+        out = np.zeros(3, np.float32)
+        for q, want in zip(g["normal_in"], g["normal_out"]):
+            L.orc_calc_normal_g(C.byref(oc), oo, n, int(q[3]), f32p(q[:3]), f32p(out))
+            assert np.array_equal(out, want)
+    if "raycast" in g:                                         # raycast: hit flag + final position
+        rec = np.zeros(7, np.float32)
+        for row in g["raycast"]:
+            L.orc_raycast_g(C.byref(oc), oo, n, f32p(row[0:3]), f32p(row[3:6]), f32p(rec))
+            pos = row[8:11] if name == "cornell_box" else row[7:10]
+            assert rec[0] == row[6] and np.array_equal(rec[4:7], pos)
+    if "bunny_sd" in g:                                        # sd_bunny, bunny_sdf_glass.py:149-203
+        for p, want in zip(g["bunny_points"], g["bunny_sd"]):
+            assert np.float32(L.orc_sd_bunny(f32p(p))) == want
+    if "sky_vals" in g:                                        # sky_color -> sample_spherical_map -> texture
+        out = np.zeros(3, np.float32)
+        for d_, want in zip(g["sky_dirs"], g["sky_vals"]):
+            L.orc_sky_envmap(f32p(env), env.shape[0], env.shape[1], f32p(d_), f32p(out))
+            assert np.array_equal(out, want)
+    if "env_table" in g:                                       # Image.process
+        assert np.array_equal(env, g["env_table"])
+
+
+def test_oracle_family_c_matches_reference_source():
+    # src/: kernel pathtrace() x launches with ray_buffer state carried between launches
+    g, oc, oo, env = oracle_of("src_scene")
+    W, H = int(g["width"]), int(g["height"])
+    rb = np.zeros((W, H, 10), np.float32)
+    img = po.pathtrace(oc, oo, 1, env=env, ray_buffer=rb)
+    assert np.array_equal(img, g["image_buffer_first"])
+    img = po.pathtrace(oc, oo, int(g["launches"]) - 1, sample_base=1, env=env, ray_buffer=rb, image_buffer=img)
+    assert np.array_equal(img, g["image_buffer"])
+    assert np.array_equal(rb.view(np.int32), g["ray_buffer"].view(np.int32))
+    assert img[..., 3].sum() > 0 and (g["ray_buffer"][..., 9].view(np.int32) < 0).any()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", SHORTEST, ids=os.path.basename)
 def test_cuda_image_buffer_matches_reference_source(path):

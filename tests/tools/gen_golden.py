@@ -73,7 +73,7 @@ def load_script(relpath: str, name: str, subs):
     mod = types.ModuleType(name)
     mod.__file__ = path
     sys.modules[name] = mod
-    exec(compile(src, path, "exec"), mod.__dict__)
+    exec(compile(src, path, "exec", dont_inherit=True), mod.__dict__)
     return mod
 
 
@@ -140,10 +140,298 @@ def gen_shortest(name, width, height, bounces, spp, seed):
     return out
 
 
+# ------------------------------------------------------------------------------ families B / C
+def synthetic_env(w=16, h=8, seed=3):
+    """Stand-in for ti.tools.imread(<.hdr>): uint8 (W, H, 3) like stb's LDR conversion returns
+    (SURVEY.md 8(c)); small and seeded so the fixture stays tiny."""
+    return np.random.default_rng(seed).integers(0, 256, size=(w, h, 3), dtype=np.uint8)
+
+
+def run_samples(m, fn, args, spp, out):
+    bufs = []
+    for s in range(spp):
+        ti.rng.launch = s
+        fn(*args)
+        bufs.append(m.image_buffer.to_numpy())
+    out["image_buffer"] = bufs[-1]
+    out["image_buffer_first"] = bufs[0]
+
+
+def probe_functions(m, out, nobj, pts, normal_pts, rays, raycast_fields):
+    """Function-level vectors shared by the family-B scripts (signed_distance / calc_normal / raycast)."""
+    sd = np.zeros((len(pts), nobj), np.float32)
+    for a, p in enumerate(pts):
+        for k in range(nobj):
+            sd[a, k] = m.signed_distance(m.objects[k], vec3(*p.tolist()))
+    out["sd_points"], out["sd_values"] = pts, sd
+    out["normal_in"] = normal_pts
+    out["normal_out"] = np.array([vlist(m.calc_normal(m.objects[int(q[3])], vec3(*q[:3].tolist()))) for q in normal_pts])
+    rows = []
+    for o, d in rays:
+        rec = m.raycast(m.Ray(vec3(*o.tolist()), vec3(*d.tolist()), vec3(1)))
+        rows.append(np.concatenate([o, d, raycast_fields(rec)]))
+    out["raycast"] = np.array(rows, np.float32)
+
+
+def random_rays(rnd, n, origin_z, spread, target_box):
+    rays = []
+    for _ in range(n):
+        o = np.array([rnd.uniform(-spread, spread), rnd.uniform(-spread, spread), origin_z], np.float32)
+        t = np.array([rnd.uniform(-1, 1) * target_box, rnd.uniform(-1, 1) * target_box, rnd.uniform(-1, 0.5) * target_box], np.float32)
+        d = vlist(ti.math.normalize(vec3(*(t - o).tolist())))
+        rays.append((o, d))
+    return rays
+
+
+def gen_cornell_box(name, width, height, bounces, spp, seed):
+    """examples/cornell_box/cornell_box.py (family B, plain marcher, PBR materials)."""
+    subs = [("image_resolution = (1920 // 4, 1920 // 4)", f"image_resolution = ({width}, {height})"),
+            ("MAX_RAYTRACE = 128", f"MAX_RAYTRACE = {bounces}")]
+    m = load_script("examples/cornell_box/cornell_box.py", f"ref_cornell_box_{name}", subs)
+    install_rng(seed)
+    rnd = np.random.default_rng(77)
+    out = {"width": width, "height": height, "bounces": bounces, "spp": spp, "seed": seed,
+           "lookfrom": np.array([0, 0, 3], np.float32), "lookat": np.array([0, 0, -1], np.float32)}
+    pts = rnd.uniform(-1.1, 1.1, (10, 3)).astype(np.float32)
+    npts = np.array([[0.6, -0.8, 0.6, 2], [-0.8, 0.1, 0.2, 3], [0.1, 0.799, 0.05, 7], [0.3, -0.3, 0.45, 6]], np.float32)
+    probe_functions(m, out, 8, pts, npts, random_rays(rnd, 6, 3.0, 0.5, 0.9),
+                    lambda rec: np.concatenate([[float(rec.hit), rec.distance], vlist(rec.position)]))
+    t0 = time.time()
+    run_samples(m, m.render, (vec3(0, 0, 3), vec3(0, 0, -1), vec3(0, 1, 0), False), spp, out)
+    out["image_pixels"] = m.image_pixels.to_numpy()
+    print(f"  {name}: {width}x{height}x{spp} spp in {time.time() - t0:.1f} s")
+    return out
+
+
+def gen_cornell_v3(name, width, height, bounces, spp, seed):
+    """examples/cornell_box/cornell_box_v3/ (family B, x10 world, rounded boxes, enhanced marcher)."""
+    d = "examples/cornell_box/cornell_box_v3"
+    names = ["config", "dataclass", "util", "scene", "sdf", "pbr", "pathtracer", "postprocessor", "renderer"]
+    for n in names:
+        sys.modules.pop(n, None)
+    load_script(f"{d}/config.py", "config", [("image_resolution = (512, 512)", f"image_resolution = ({width}, {height})"),
+                                             ("MAX_RAYTRACE = 3", f"MAX_RAYTRACE = {bounces}")])
+    sys.path.insert(0, os.path.join(REF, d))
+    try:
+        import renderer as m
+        import pathtracer as pt
+        import scene as sc
+        import sdf as sdfm
+    finally:
+        sys.path.pop(0)
+    install_rng(seed)
+    rnd = np.random.default_rng(78)
+    out = {"width": width, "height": height, "bounces": bounces, "spp": spp, "seed": seed,
+           "lookfrom": np.array([0, 0, 35], np.float32), "lookat": np.array([0, 0, -10], np.float32)}
+    pts = (rnd.uniform(-1.1, 1.1, (8, 3)) * 10).astype(np.float32)
+    sd = np.zeros((len(pts), 8), np.float32)
+    for a, p in enumerate(pts):
+        for k in range(8):
+            sd[a, k] = sdfm.signed_distance(sc.objects[k], vec3(*p.tolist()))
+    out["sd_points"], out["sd_values"] = pts, sd
+    rows = []
+    for o, dd in random_rays(rnd, 6, 35.0, 5.0, 9.0):
+        rec = pt.raycast(pt.Ray(vec3(*o.tolist()), vec3(*dd.tolist()), vec3(1)))
+        rows.append(np.concatenate([o, dd, [float(rec.hit)], vlist(rec.position)]))
+    out["raycast"] = np.array(rows, np.float32)
+    t0 = time.time()
+    bufs = []
+    for s in range(spp):
+        ti.rng.launch = s
+        m.render(vec3(0, 0, 35), vec3(0, 0, -10), vec3(0, 1, 0), False)
+        bufs.append(sc.image_buffer.to_numpy())
+    out["image_buffer"], out["image_buffer_first"] = bufs[-1], bufs[0]
+    out["image_pixels"] = sc.image_pixels.to_numpy()
+    for n in names:
+        sys.modules.pop(n, None)
+    print(f"  {name}: {width}x{height}x{spp} spp in {time.time() - t0:.1f} s")
+    return out
+
+
+def gen_tokyo(name, width, height, spp, seed, script="tokyo_ibl"):
+    """examples/scene_demo/tokyo_ibl.py (or main.py): 7-object scene, enhanced marcher, IBL / gradient sky."""
+    env_u8 = synthetic_env()
+    ti.tools.imread = lambda path: env_u8
+    if script == "tokyo_ibl":
+        subs = [("image_resolution = (192*15, 108*15)", f"image_resolution = ({width}, {height})")]
+    else:
+        subs = [("image_resolution = (1920 // 4, 1080 // 4)", f"image_resolution = ({width}, {height})")]
+    m = load_script(f"examples/scene_demo/{'tokyo_ibl' if script == 'tokyo_ibl' else 'main'}.py", f"ref_{script}_{name}", subs)
+    m.init_scene()
+    install_rng(seed)
+    rnd = np.random.default_rng(79)
+    out = {"width": width, "height": height, "spp": spp, "seed": seed, "env_u8": env_u8,
+           "lookfrom": np.array([0, -0.2, 4], np.float32), "lookat": np.array([0, -0.2, 3], np.float32)}
+    if script == "tokyo_ibl":
+        out["env_table"] = m.hdr_map.img.to_numpy()
+        dirs = rnd.normal(size=(12, 3))
+        dirs = np.array([vlist(ti.math.normalize(vec3(*d.tolist()))) for d in dirs] + [[0, -1, 0], [1, 0, 0], [0, 0, -1], [0, 0, 1]], np.float32)   # (0,1,0) and (-1,0,0) index out of bounds in the reference (v == 1, u == 1)
+        out["sky_dirs"] = dirs
+        out["sky_vals"] = np.array([vlist(m.sky_color(m.Ray(vec3(0), vec3(*d.tolist()), vec3(1)))) for d in dirs], np.float32)
+    pts = (rnd.uniform(-1.5, 1.5, (10, 3)) * [1, 0.5, 2]).astype(np.float32)
+    sd = np.zeros((len(pts), 7), np.float32)
+    near = np.zeros((len(pts), 2), np.float32)
+    for a, p in enumerate(pts):
+        for k in range(7):
+            sd[a, k] = m.signed_distance(m.objects[k], vec3(*p.tolist()))
+        idx, dis = m.nearest_object(vec3(*p.tolist()))
+        near[a] = [idx, dis]
+    out["sd_points"], out["sd_values"], out["nearest"] = pts, sd, near
+    npts = np.array([[0.0, 0.5, 0.0, 1], [1.0, 0.1, 0.0, 2], [-1.0, 0.1, 0.0, 4], [0.5, 0.3, -1.77, 6], [0.3, -0.501, 0.7, 0]], np.float32)
+    out["normal_in"] = npts
+    out["normal_out"] = np.array([vlist(m.calc_normal(m.objects[int(q[3])], vec3(*q[:3].tolist()))) for q in npts])
+    rows = []
+    for o, d in random_rays(rnd, 8, 4.0, 0.3, 1.2):
+        obj, position, hit = m.raycast(m.Ray(vec3(*o.tolist()), vec3(*d.tolist()), vec3(1)))
+        rows.append(np.concatenate([o, d, [float(hit)], vlist(position), vlist(obj.material.albedo)]))
+    out["raycast"] = np.array(rows, np.float32)
+    t0 = time.time()
+    run_samples(m, m.sample, (vec3(0, -0.2, 4), vec3(0, -0.2, 3), vec3(0, 1, 0)), spp, out)
+    m.render()
+    out["image_pixels"] = m.image_pixels.to_numpy()
+    print(f"  {name}: {width}x{height}x{spp} spp in {time.time() - t0:.1f} s")
+    return out
+
+
+def gen_bunny(name, width, height, bounces, spp, seed, frame):
+    """examples/bunny/bunny_sdf_glass.py: neural SDF, glass, w = 0.5 marcher, env map ^2.2 at lookup."""
+    env_u8 = synthetic_env(seed=5)
+    ti.tools.imread = lambda path: env_u8
+    subs = [("image_resolution = (1920, 1080)", f"image_resolution = ({width}, {height})"),
+            ("MAX_RAYTRACE = 512", f"MAX_RAYTRACE = {bounces}"),
+            ("while True:", "while False:")]
+    m = load_script("examples/bunny/bunny_sdf_glass.py", f"ref_bunny_{name}", subs)
+    install_rng(seed)
+    rnd = np.random.default_rng(80)
+    out = {"width": width, "height": height, "bounces": bounces, "spp": spp, "seed": seed, "frame": frame, "env_u8": env_u8,
+           "lookfrom": np.array([0, 0, 4], np.float32), "lookat": np.array([0, 0, 3], np.float32)}
+    pts = rnd.uniform(-0.7, 0.7, (24, 3)).astype(np.float32)
+    pts[:4] *= 2.5                                       # some outside the unit sphere
+    out["bunny_points"] = pts
+    out["bunny_sd"] = np.array([m.sd_bunny(vec3(*p.tolist())) for p in pts], np.float32)
+    m.u_frame[None] = frame
+    out["sd_values"] = np.array([[m.signed_distance(m.objects[0], vec3(*p.tolist()))] for p in pts], np.float32)
+    out["sd_points"] = pts
+    dirs = np.array([vlist(ti.math.normalize(vec3(*d.tolist()))) for d in rnd.normal(size=(8, 3))], np.float32)
+    out["sky_dirs"] = dirs
+    out["sky_vals"] = np.array([vlist(m.sky_color(m.Ray(vec3(0), vec3(*d.tolist()), vec3(1)))) for d in dirs], np.float32)
+    t0 = time.time()
+    run_samples(m, m.sample, (vec3(0, 0, 4), vec3(0, 0, 3), vec3(0, 1, 0), frame), spp, out)
+    print(f"  {name}: {width}x{height}x{spp} spp in {time.time() - t0:.1f} s")
+    return out
+
+
+class _SrcFinder:
+    """Imports `src.*` from the reference tree, applying parameter substitutions to src/config.py."""
+    def __init__(self, subs):
+        self.subs = subs
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.util
+        if fullname != "src" and not fullname.startswith("src."):
+            return None
+        rel = fullname.replace(".", "/")
+        base = os.path.join(REF, rel)
+        if os.path.isdir(base):
+            spec = importlib.util.spec_from_loader(fullname, self, is_package=True)
+            spec.submodule_search_locations = [base]
+            spec.origin = os.path.join(base, "__init__.py")
+            return spec
+        spec = importlib.util.spec_from_loader(fullname, self)
+        spec.origin = base + ".py"
+        return spec
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        path = module.__spec__.origin
+        if not os.path.exists(path):
+            return                                          # namespace-like package without __init__.py
+        src = open(path).read()
+        for old, new in self.subs.get(module.__name__, []):
+            if src.count(old) != 1:
+                raise SystemExit(f"{path}: substitution target {old!r} found {src.count(old)} times")
+            src = src.replace(old, new)
+        module.__file__ = path
+        exec(compile(src, path, "exec", dont_inherit=True), module.__dict__)
+
+
+def gen_src(name, width, height, launches, seed, spp_per_launch=1):
+    """src/ package (family C): kernel pathtrace() x launches, ray_buffer state persisted between launches."""
+    env_u8 = synthetic_env(seed=9)
+    ti.tools.imread = lambda path: env_u8
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    subs = {"src.config": [("image_resolution = (1920 * 4 // 10, 1080 * 4 // 10)", f"image_resolution = ({width}, {height})"),
+                           ("SAMPLES_PER_PIXEL = 1  #", f"SAMPLES_PER_PIXEL = {spp_per_launch}  #")]}
+    finder = _SrcFinder(subs)
+    sys.meta_path.insert(0, finder)
+    try:
+        import src.renderer as rend
+        import src.pathtracer as pt
+        import src.scene as sc
+        import src.camera as cam
+        import src.fileds as fld
+        import src.ibl as ibl
+        import src.pbr  # noqa: F401
+    finally:
+        sys.meta_path.remove(finder)
+    cam.smooth.position[None] = vec3(0, -0.2, 4.0)             # src/main.py:17 camera.position(0, -0.2, 4.0)
+    cam.smooth.lookat[None] = vec3(0, -0.2, 3.0)
+    cam.smooth.up[None] = vec3(0, 1, 0)
+    sc.build_scene()
+    install_rng(seed)
+    rnd = np.random.default_rng(81)
+    out = {"width": width, "height": height, "launches": launches, "seed": seed, "env_u8": env_u8, "spp_per_launch": spp_per_launch,
+           "lookfrom": np.array([0, -0.2, 4], np.float32), "lookat": np.array([0, -0.2, 3], np.float32),
+           "env_table": ibl.hdr_map.img.to_numpy()}
+    pts = (rnd.uniform(-1.5, 1.5, (10, 3)) * [1, 0.5, 2]).astype(np.float32)
+    near = np.zeros((len(pts), 2), np.float32)
+    for a, p in enumerate(pts):
+        idx, dis = sc.nearest(vec3(*p.tolist()))
+        near[a] = [idx, dis]
+    out["sd_points"], out["nearest"] = pts, near
+    npts = np.array([[0.0, 0.5, 0.0, 1], [1.0, 0.1, 0.0, 2], [-1.0, 0.1, 0.0, 4], [0.5, 0.3, -1.77, 6], [0.3, -0.501, 0.7, 0]], np.float32)
+    out["normal_in"] = npts
+    out["normal_out"] = np.array([vlist(sc.calc_normal(sc.objects[int(q[3])], vec3(*q[:3].tolist()))) for q in npts])
+    rows = []
+    for o, d in random_rays(rnd, 8, 4.0, 0.3, 1.2):
+        ray, obj, hit = sc.raycast(pt.Ray(vec3(*o.tolist()), vec3(*d.tolist()), vec3(1), 0))
+        rows.append(np.concatenate([o, d, [float(hit)], vlist(ray.origin), vlist(obj.material.albedo)]))
+    out["raycast"] = np.array(rows, np.float32)
+    t0 = time.time()
+    rend.refresh()
+    snaps = {}
+    for L in range(launches):
+        ti.rng.launch = L
+        pt.pathtrace()
+        if L in (0, launches // 2):
+            snaps[L] = fld.image_buffer.to_numpy()
+    out["image_buffer"] = fld.image_buffer.to_numpy()
+    out["image_buffer_first"] = snaps[0]
+    rb = np.zeros((width, height, 10), np.float32)
+    rb[..., 0:3] = fld.ray_buffer.member("origin")
+    rb[..., 3:6] = fld.ray_buffer.member("direction")
+    rb[..., 6:9] = fld.ray_buffer.member("color")
+    rb[..., 9] = fld.ray_buffer.member("depth").astype(np.int32).view(np.float32)
+    out["ray_buffer"] = rb
+    rend.post_process()
+    out["image_pixels"] = fld.image_pixels.to_numpy()
+    print(f"  {name}: {width}x{height} x {launches} launches in {time.time() - t0:.1f} s")
+    return out
+
+
 FIXTURES = {
     # name: (generator, kwargs)
     "shortest_3b": (gen_shortest, dict(width=12, height=10, bounces=3, spp=2, seed=0)),      # the file as shipped (3 bounces)
     "shortest_8b": (gen_shortest, dict(width=10, height=8, bounces=8, spp=2, seed=7)),       # BASELINE configs[1] bounce count
+    "cornell_box": (gen_cornell_box, dict(width=8, height=8, bounces=6, spp=2, seed=1)),
+    "cornell_v3": (gen_cornell_v3, dict(width=8, height=8, bounces=3, spp=2, seed=2)),
+    "tokyo_ibl": (gen_tokyo, dict(width=12, height=8, spp=3, seed=3)),
+    "scene_demo": (gen_tokyo, dict(width=8, height=6, spp=2, seed=4, script="main")),
+    "bunny_glass": (gen_bunny, dict(width=8, height=6, bounces=16, spp=1, seed=5, frame=7)),
+    "src_scene": (gen_src, dict(width=10, height=6, launches=12, seed=6)),
 }
 
 

@@ -15,7 +15,7 @@ import itertools as _it
 import numpy as _np
 
 from . import math  # noqa: F401
-from ._scalar import F, r32
+from ._scalar import F, I, r32
 from .math import Mat, Vec, mat2, mat3, mat4, vec2, vec3, vec4
 
 f32 = float
@@ -61,7 +61,7 @@ def _cast(tp, v):
     if tp is float or tp is f32:
         return F(v)
     if tp is int:
-        return int(v)
+        return I(int(v))
     if tp is bool:
         return bool(v)
     if isinstance(tp, type) and issubclass(tp, Vec):
@@ -77,7 +77,7 @@ def _zero(tp):
     if tp is float or tp is f32:
         return F(0.0)
     if tp is int:
-        return 0
+        return I(0)
     if tp is bool:
         return False
     return tp()

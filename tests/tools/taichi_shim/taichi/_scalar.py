@@ -105,6 +105,43 @@ class F(float):
         return f"F({float.__repr__(self)})"
 
 
+class I(int):
+    """Run-time i32 value (struct members, field elements).  Arithmetic with a float yields an
+    F -- Taichi casts the i32 to f32 and computes in f32 -- so expressions such as
+    `ray.depth * (1.0 / MAX_RAYTRACE)` (src/pathtracer.py:68) are rounded like the reference."""
+    __slots__ = ()
+
+    def _wrap(self, r, o):
+        if r is NotImplemented:
+            return r
+        return I(r) if isinstance(o, int) and not isinstance(o, bool) or isinstance(o, bool) else r
+
+    def __add__(self, o):
+        return F(int(self)) + o if isinstance(o, float) else I(int.__add__(self, o))
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return F(int(self)) - o if isinstance(o, float) else I(int.__sub__(self, o))
+
+    def __rsub__(self, o):
+        return o - F(int(self)) if isinstance(o, float) else I(int.__rsub__(self, o))
+
+    def __mul__(self, o):
+        return F(int(self)) * o if isinstance(o, float) else I(int.__mul__(self, o))
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return F(int(self)) / o
+
+    def __rtruediv__(self, o):
+        return F(o) / F(int(self))
+
+    def __neg__(self):
+        return I(int.__neg__(self))
+
+
 def _ok(o):
     return isinstance(o, (int, float, bool))
 
