@@ -19,7 +19,7 @@ Legs
   e2e           the same step through the public Python API (raytracingpbr_b200.PathTracer) with
                 HOST buffers: scene + camera structs copied host->device and the accumulation
                 buffer copied device->host inside the timed region, every step.
-  roofline      dominant kernel (k_pathtrace_persistent) timed with CUDA events on its launch
+  roofline      dominant kernel (k_pathtrace_pool) timed with CUDA events on its launch
                 stream: algorithmic HBM bytes / duration against MEASURED_PEAKS.json, plus the
                 counted-work FP32 figure that actually bounds this path.
   cpu_baseline  the CPU oracle (oracle/oracle.c; stand-in for "Taichi ti.cpu", which cannot be
@@ -291,7 +291,7 @@ def main() -> int:
     local_pixels = W * H / world
     alg_bytes = BYTES_PER_PIXEL_PER_LAUNCH * local_pixels
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_pathtrace_persistent" if kernel == N.KERNEL_PERSISTENT else "k_pathtrace_simple",
+    roof = {"bound": "hbm", "kernel": "k_pathtrace_pool" if kernel == N.KERNEL_PERSISTENT else "k_pathtrace_simple",
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
             "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "kernel_share_of_step": kernel_ms_max / ms,
             "note": "this path is FP32-issue bound, not HBM bound (32 B per pixel per launch); see fp32"}

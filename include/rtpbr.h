@@ -61,8 +61,8 @@ enum { RTPBR_MARCH_PLAIN = 0,      /* cornell_box_shortest.py:63-72, cornell_box
 
 enum { RTPBR_SKY_BLACK = 0, RTPBR_SKY_ENVMAP = 1, RTPBR_SKY_GRADIENT = 2 };
 
-enum { RTPBR_KERNEL_PERSISTENT = 0,  /* persistent-threads wavefront kernel (default)        */
-       RTPBR_KERNEL_SIMPLE = 1 };    /* one thread per pixel, no regeneration (validation)   */
+enum { RTPBR_KERNEL_PERSISTENT = 0,  /* persistent wavefront kernel with per-warp path pools (default) */
+       RTPBR_KERNEL_SIMPLE = 1 };    /* one thread per pixel, run to completion (validation)          */
 
 /* Flattened src/dataclass.py:13-35 (Material, Transform, SDFObject). `Transform.matrix`
  * is derived by rtpbr_set_scene (replaces kernel update_all_transform, src/scene.py:99-109). */
@@ -132,7 +132,9 @@ enum { RTPBR_BUF_IMAGE_BUFFER = 0,  /* image_buffer  vec4 f32 (W,H,4), src/filed
 enum { RTPBR_CNT_SCENE_EVALS = 0, RTPBR_CNT_RAYS = 1, RTPBR_CNT_NORMALS = 2, RTPBR_CNT_SAMPLES = 3,
        RTPBR_CNT_MARCH_ITERS = 4,      /* warp-level march iterations x 32 (issued lane slots) */
        RTPBR_CNT_MARCH_ACTIVE = 5,     /* lanes actually marching in those iterations         */
-       RTPBR_CNT_RESOLVE_ROUNDS = 6, RTPBR_CNT_LAUNCHES = 7, RTPBR_CNT_COUNT = 8 };
+       RTPBR_CNT_RESOLVE_ROUNDS = 6, RTPBR_CNT_LAUNCHES = 7,
+       RTPBR_CNT_RESOLVED_SLOTS = 8,   /* slots handled by resolve rounds (x / rounds / 32 = resolve occupancy) */
+       RTPBR_CNT_COUNT = 10 };
 
 /* replaces `ti.init(arch=ti.gpu, ...)` (src/config.py:5) + field allocation (src/fileds.py:7-13) */
 RTPBR_API int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out);

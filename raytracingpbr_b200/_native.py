@@ -24,7 +24,8 @@ MARCH_PLAIN, MARCH_ENHANCED, MARCH_SRC = 0, 1, 2
 SKY_BLACK, SKY_ENVMAP, SKY_GRADIENT = 0, 1, 2
 KERNEL_PERSISTENT, KERNEL_SIMPLE = 0, 1
 BUF_IMAGE_BUFFER, BUF_IMAGE_PIXELS, BUF_RAY_BUFFER = 0, 1, 2
-CNT_NAMES = ("scene_evals", "rays", "normals", "samples", "march_iters", "march_active", "resolve_rounds", "launches")
+CNT_NAMES = ("scene_evals", "rays", "normals", "samples", "march_iters", "march_active", "resolve_rounds", "launches",
+             "resolved_slots", "reserved")
 
 EXPORTS = (
     "rtpbr_create", "rtpbr_destroy", "rtpbr_set_scene", "rtpbr_set_camera", "rtpbr_set_envmap", "rtpbr_set_frame",
@@ -228,7 +229,7 @@ class Context:
 
     # -- data -------------------------------------------------------------------------
     def download(self, which: int = BUF_IMAGE_BUFFER, out: np.ndarray | None = None) -> np.ndarray:
-        ch = 4 if which == BUF_IMAGE_BUFFER else 3
+        ch = {BUF_IMAGE_BUFFER: 4, BUF_IMAGE_PIXELS: 3, BUF_RAY_BUFFER: 10}[which]
         if out is None:
             out = np.empty((self.width, self.height, ch), dtype=np.float32)
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.width, self.height, ch)

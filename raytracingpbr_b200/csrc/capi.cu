@@ -81,12 +81,13 @@ struct RtpbrContext {
     size_t kernel_events_used = 0;
     float4* d_image_buffer = nullptr;
     float* d_image_pixels = nullptr;
+    float* d_ray_buffer = nullptr;
     float* d_rr = nullptr;
     float* d_env = nullptr;
     unsigned int* d_work = nullptr;
     unsigned long long* d_counters = nullptr;
     void* d_flush = nullptr;
-    bool have_scene = false, have_camera = false;
+    bool have_scene = false, have_camera = false, has_bunny = false;
     uint32_t sample_base = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0, blocks_per_sm = 0;
     void* nccl_comm = nullptr;
@@ -102,7 +103,9 @@ rt::KernelSelect select_kernel(const RtpbrContext* c)
 {
     rt::KernelSelect s;
     s.family = c->cfg.family;
+    s.marcher = c->cfg.marcher;
     s.nobj = c->P.nobj;
+    s.bunny = c->has_bunny;
     s.count = c->cfg.count_work != 0;
     return s;
 }
@@ -115,7 +118,15 @@ int validate_config(const RtpbrConfig& c)
     if (c.max_bounces < 1 || c.max_bounces > RTPBR_MAX_BOUNCES) return fail(RTPBR_ERR_ARG, "bad max_bounces");
     if (c.max_steps < 1) return fail(RTPBR_ERR_ARG, "bad max_steps");
     if (!(c.light_quality > 0.f)) return fail(RTPBR_ERR_ARG, "bad light_quality");
-    if (c.family != RTPBR_FAMILY_A) return fail(RTPBR_ERR_UNSUPPORTED, "only family A is implemented in this build");
+    if (c.marcher < RTPBR_MARCH_PLAIN || c.marcher > RTPBR_MARCH_SRC) return fail(RTPBR_ERR_ARG, "bad marcher");
+    if (c.family == RTPBR_FAMILY_A && (c.marcher != RTPBR_MARCH_PLAIN || c.box_round != 0.f || c.bsdf != 0))
+        return fail(RTPBR_ERR_ARG, "family A (cornell_box_shortest.py) is plain marching, sharp boxes, diffuse only");
+    if (c.family == RTPBR_FAMILY_B && (c.marcher == RTPBR_MARCH_SRC || c.bsdf != 1))
+        return fail(RTPBR_ERR_UNSUPPORTED, "family B uses the plain or enhanced marcher and bsdf 1");
+    if (c.family == RTPBR_FAMILY_C && (c.marcher != RTPBR_MARCH_SRC || c.bsdf != 2))
+        return fail(RTPBR_ERR_UNSUPPORTED, "family C (src/) uses the src marcher and bsdf 2");
+    if (c.family == RTPBR_FAMILY_C && c.samples_per_pixel < 1) return fail(RTPBR_ERR_ARG, "bad samples_per_pixel");
+    if (c.sky < RTPBR_SKY_BLACK || c.sky > RTPBR_SKY_GRADIENT) return fail(RTPBR_ERR_ARG, "bad sky");
     return RTPBR_OK;
 }
 
@@ -156,10 +167,11 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     c->cc_minor = prop.minor;
     rt::fill_config(c->P, c->cfg);
     rt::fill_shard(c->P, 0, 1, 32);
-    c->P.resolve_q = 8;
-    if (const char* q = getenv("RTPBR_RESOLVE_Q")) {
+    rt::fill_frame(c->P, 0);
+    c->P.resolve_min = 8;
+    if (const char* q = getenv("RTPBR_RESOLVE_MIN")) {
         int v = atoi(q);
-        if (v >= 1 && v <= 32) c->P.resolve_q = v;
+        if (v >= 1 && v <= 32) c->P.resolve_min = v;
     }
 #define CREATE_TRY(expr)                                                                            \
     do {                                                                                            \
@@ -179,6 +191,10 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     CREATE_TRY(cudaMalloc(&c->d_counters, RTPBR_CNT_COUNT * sizeof(unsigned long long)));
     CREATE_TRY(cudaMemsetAsync(c->d_image_buffer, 0, n * sizeof(float4), c->stream));
     CREATE_TRY(cudaMemsetAsync(c->d_image_pixels, 0, n * 3 * sizeof(float), c->stream));
+    if (cfg->family == RTPBR_FAMILY_C) {   // ray_buffer = Ray.field(), zero-initialised like a fresh Taichi field
+        CREATE_TRY(cudaMalloc(&c->d_ray_buffer, n * 10 * sizeof(float)));
+        CREATE_TRY(cudaMemsetAsync(c->d_ray_buffer, 0, n * 10 * sizeof(float), c->stream));
+    }
     CREATE_TRY(cudaMemsetAsync(c->d_counters, 0, RTPBR_CNT_COUNT * sizeof(unsigned long long), c->stream));
     std::vector<float> rr = rt::rr_table(c->cfg);
     CREATE_TRY(cudaMalloc(&c->d_rr, rr.size() * sizeof(float)));
@@ -186,6 +202,7 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     CREATE_TRY(cudaStreamSynchronize(c->stream));
 #undef CREATE_TRY
     c->P.image_buffer = c->d_image_buffer;
+    c->P.ray_buffer = c->d_ray_buffer;
     c->P.rr_prob = c->d_rr;
     c->P.env = nullptr;
     c->P.env_w = c->P.env_h = 0;
@@ -206,6 +223,7 @@ int rtpbr_destroy(RtpbrContext* c)
     if (c->ev_stop) cudaEventDestroy(c->ev_stop);
     cudaFree(c->d_image_buffer);
     cudaFree(c->d_image_pixels);
+    cudaFree(c->d_ray_buffer);
     cudaFree(c->d_rr);
     cudaFree(c->d_env);
     cudaFree(c->d_work);
@@ -220,13 +238,21 @@ int rtpbr_set_scene(RtpbrContext* c, const RtpbrObject* objects, int n)
 {
     if (!c || !objects) return fail(RTPBR_ERR_ARG, "null argument");
     if (n < 1 || n > RTPBR_MAX_OBJECTS) return fail(RTPBR_ERR_ARG, "object count must be in 1..RTPBR_MAX_OBJECTS");
+    bool bunny = false;
     for (int k = 0; k < n; ++k) {
         if (objects[k].type < RTPBR_SHAPE_NONE || objects[k].type > RTPBR_SHAPE_BUNNY)
             return fail(RTPBR_ERR_ARG, "bad shape type");
         if (c->cfg.family == RTPBR_FAMILY_A && objects[k].type != RTPBR_SHAPE_BOX)
             return fail(RTPBR_ERR_ARG, "family A (cornell_box_shortest.py) scenes are boxes only");
+        bunny = bunny || objects[k].type == RTPBR_SHAPE_BUNNY;
     }
+    rt::KernelSelect sel = select_kernel(c);
+    sel.bunny = bunny;
+    if (!rt::kernel_supported(sel))
+        return fail(RTPBR_ERR_UNSUPPORTED, "no kernel variant for this family / marcher / shape combination "
+                                           "(the neural bunny needs family B with the enhanced marcher)");
     rt::fill_objects(c->P, objects, n);
+    c->has_bunny = bunny;
     c->have_scene = true;
     c->blocks_per_sm = 0;  // kernel variant may change with the object count
     return RTPBR_OK;
@@ -260,7 +286,7 @@ int rtpbr_set_envmap(RtpbrContext* c, const float* rgb, int w, int h)
 int rtpbr_set_frame(RtpbrContext* c, int frame)
 {
     if (!c) return fail(RTPBR_ERR_ARG, "null context");
-    c->P.frame = frame;
+    rt::fill_frame(c->P, frame);
     return RTPBR_OK;
 }
 
@@ -284,6 +310,7 @@ int rtpbr_refresh(RtpbrContext* c)
     if (!c) return fail(RTPBR_ERR_ARG, "null context");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemsetAsync(c->d_image_buffer, 0, npixels(c) * sizeof(float4), c->stream));
+    if (c->d_ray_buffer) CUDA_TRY(rt::launch_refresh_depth(c->d_ray_buffer, (int)npixels(c), c->stream));
     return RTPBR_OK;
 }
 
@@ -313,15 +340,17 @@ int rtpbr_pathtrace(RtpbrContext* c, int spp)
         CUDA_TRY(cudaEventRecord(ev.second, c->stream));
     } else {
         if (c->blocks_per_sm == 0) {
-            CUDA_TRY(rt::persistent_occupancy(sel, &c->blocks_per_sm));
-            if (c->blocks_per_sm < 1) return fail(RTPBR_ERR_CUDA, "persistent kernel does not fit on an SM");
+            CUDA_TRY(rt::pool_occupancy(sel, &c->blocks_per_sm));
+            if (c->blocks_per_sm < 1) return fail(RTPBR_ERR_CUDA, "pool kernel does not fit on an SM");
         }
         int grid = c->sm_count * c->blocks_per_sm;
-        const long long need = ((long long)c->P.total_work + rt::kPersistentBlock - 1) / rt::kPersistentBlock;
+        // one CTA keeps (warps x pool slots) pixels in flight
+        const long long per_cta = (long long)(rt::kPoolBlock / 32) * rt::kPoolSlots;
+        const long long need = ((long long)c->P.total_work + per_cta - 1) / per_cta;
         if ((long long)grid > need) grid = (int)need;
         CUDA_TRY(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->stream));
         CUDA_TRY(cudaEventRecord(ev.first, c->stream));
-        CUDA_TRY(rt::launch_pathtrace_persistent(sel, c->P, grid, c->stream));
+        CUDA_TRY(rt::launch_pathtrace_pool(sel, c->P, grid, c->stream));
         CUDA_TRY(cudaEventRecord(ev.second, c->stream));
     }
     c->kernel_events_used++;
@@ -345,6 +374,9 @@ static int buffer_of(RtpbrContext* c, int which, void** ptr, size_t* bytes)
     switch (which) {
     case RTPBR_BUF_IMAGE_BUFFER: *ptr = c->d_image_buffer; *bytes = npixels(c) * sizeof(float4); return RTPBR_OK;
     case RTPBR_BUF_IMAGE_PIXELS: *ptr = c->d_image_pixels; *bytes = npixels(c) * 3 * sizeof(float); return RTPBR_OK;
+    case RTPBR_BUF_RAY_BUFFER:
+        if (!c->d_ray_buffer) return fail(RTPBR_ERR_STATE, "ray_buffer exists in family C only");
+        *ptr = c->d_ray_buffer; *bytes = npixels(c) * 10 * sizeof(float); return RTPBR_OK;
     default: return fail(RTPBR_ERR_ARG, "unknown buffer");
     }
 }

@@ -118,10 +118,32 @@ inline void fill_config(KParams& P, const RtpbrConfig& c)
     P.relax_guard = c.relax_guard; P.relax_reset = c.relax_reset;
     P.normal_h = c.normal_h; P.box_round = c.box_round;
     P.visibility_min = c.visibility_min; P.visibility_max = c.visibility_max;
-    P.f0_variant = c.f0_variant;
+    P.bsdf = c.bsdf; P.f0_variant = c.f0_variant;
+    P.nearest_seed = c.nearest_seed; P.normal_mode = c.normal_mode;
+    P.samples_per_pixel = c.samples_per_pixel > 0 ? c.samples_per_pixel : 1;
+    P.inv_max_bounces = (float)(1.0 / (double)c.max_bounces);   // ti.static(1.0 / MAX_RAYTRACE), src/pathtracer.py:68
     P.sky = c.sky; P.sky_scale = c.sky_scale;
     P.min_dis = c.min_dis; P.pixel_radius = c.pixel_radius; P.quality_per_sample = c.quality_per_sample;
     P.black_background = c.black_background;
+}
+
+// bunny_sdf_glass.py:213-216: t = pi * float(u_frame) / 120.0; angle(vec3(0, 0, t)); 0.1 * sin(t)
+inline void fill_frame(KParams& P, int frame)
+{
+    P.frame = frame;
+    float t = kPi * (float)frame / 120.0f, sn, cs;
+    sincos_rt(t, sn, cs);
+    // angle(vec3(0, 0, t)) = Rz(t) @ I @ I evaluated with the same matrix products as euler_matrix_deg
+    const float A[9] = { cs, sn, 0, -sn, cs, 0, 0, 0, 1 };
+    const float I3[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    float AB[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            AB[3 * i + j] = fmaf(A[3 * i + 2], I3[6 + j], fmaf(A[3 * i + 1], I3[3 + j], A[3 * i] * I3[j]));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            P.anim_m[3 * i + j] = fmaf(AB[3 * i + 2], I3[6 + j], fmaf(AB[3 * i + 1], I3[3 + j], AB[3 * i] * I3[j]));
+    P.anim_bob = 0.1f * sn;
 }
 
 inline void fill_shard(KParams& P, int rank, int nranks, int band)

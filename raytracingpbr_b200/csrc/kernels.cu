@@ -1,8 +1,9 @@
 // kernels.cu -- sm_100a kernels of the path-tracing hot path.
 //
-//   k_pathtrace_persistent  persistent-threads wavefront kernel (the product path)
-//   k_pathtrace_simple      one thread per pixel, run-to-completion (validation / baseline)
-//   k_post_process          tonemap (src/postprocessor.py:24-38 and the example variants)
+//   k_pathtrace_pool    persistent wavefront kernel with a per-warp path pool (the product path)
+//   k_pathtrace_simple  one thread per pixel, run-to-completion (validation / baseline)
+//   k_refresh_depth     family C part of refresh(): ray_buffer[i, j].depth = 0
+//   k_post_process      tonemap (src/postprocessor.py:24-38 and the example variants)
 //
 // Compiled with -fmad=false: the fp32 contract (rt_math.cuh) allows only explicit fmaf().
 #include <cuda_runtime.h>
@@ -15,130 +16,297 @@ namespace rt {
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------
-// Persistent-threads wavefront kernel.
+// Wavefront pool kernel.
 //
-// Every lane owns one path at a time and walks a small state machine:
-//     FETCH -> NEWPATH -> MARCH -> (HIT -> MARCH ...) -> DONE -> NEWPATH/FETCH ... -> IDLE
-// The warp-wide loop body is ONE sphere-tracing step (scene SDF evaluation) for the lanes in
-// MARCH.  Lanes whose ray has hit / left / been terminated wait ("pending") until at least
-// resolve_q/32 of the warp's live lanes are pending (or nobody marches); then one *resolve
-// round* shades all pending hits together, accumulates finished samples, regenerates camera
-// paths in the freed lanes (path regeneration), and pulls new pixels from the global work
-// queue with one warp-aggregated atomic.  This bounds SIMT divergence in the march loop (the
-// >90% cost, heavy-tailed step counts) to 1 - resolve_q/32 idle lanes and keeps the divergent
-// shading code off the hot loop.  Samples of one pixel are traced by one lane in index order,
-// so the fp32 accumulation order equals the reference's launch-by-launch `buffer += color`
-// (cornell_box_shortest.py:121) and the result is independent of scheduling.
+// Every warp owns a pool of NSLOT path slots in shared memory (structure of arrays, one word
+// per field per slot).  A slot is a pixel worker: it traces the samples of one pixel one after
+// the other (so the fp32 accumulation order equals the reference's launch-by-launch
+// `buffer += color`), then pulls the next pixel from the global work queue.
+//
+// The warp alternates between two phases, both at (nearly) full lane occupancy:
+//   MARCH    each lane holds the march state of one slot in registers and the warp-wide loop
+//            body is ONE sphere-tracing step (scene SDF evaluation).  A lane whose ray hits /
+//            leaves / runs out of steps writes the result to its slot, pushes the slot on the
+//            warp's `pending` stack and pops a ready-to-march slot from the `ready` stack.
+//   RESOLVE  when lanes would idle (ready stack empty) the marching lanes park their slots and
+//            all 32 lanes pop pending slots: surface interaction (normal, BSDF sample,
+//            Russian roulette), sample accumulation, path regeneration, and warp-aggregated
+//            work-queue pulls.  Resolved slots go back on the ready stack.
+// With NSLOT = 64 the pool holds 32 marching + 32 ready/pending slots, so the heavy-tailed
+// march lengths (p50 28, p99 ~100 steps) no longer idle lanes, and the divergent shading code
+// runs on compacted batches.  The RNG is keyed by (pixel, sample, draw index) only, so the
+// scheduling cannot change any number a sample sees: results are bit-identical to the simple
+// kernel and to the CPU oracle.
 // ------------------------------------------------------------------------------------------
-enum : int { M_MARCH = 0, M_HIT = 1, M_DONE = 2, M_FETCH = 3, M_NEWPATH = 4, M_IDLE = 5 };
+enum : int { ST_NONE = 0, ST_READY = 1, ST_HIT = 2, ST_MISS = 3, ST_DONE = 4, ST_FETCH = 5, ST_NEWPATH = 6,
+             ST_ADVANCE = 7, ST_DEAD = 8 };
 
-template <class VAR>
-__global__ void __launch_bounds__(kPersistentBlock, kPersistentMinBlocks)
-k_pathtrace_persistent(const __grid_constant__ KParams P)
+// slot fields (word index into the per-warp SoA)
+enum : int { F_ROX = 0, F_ROY, F_ROZ, F_RDX, F_RDY, F_RDZ, F_COLX, F_COLY, F_COLZ, F_T, F_W, F_S, F_D, F_TEVAL,
+             F_STEPS, F_IDX, F_DEPTH, F_RNGN, F_PIXEL, F_SAMP, F_K, F_STATUS, F_ACCX, F_ACCY, F_ACCZ, F_ACCW,
+             F_COUNT };
+
+template <int NSLOT>
+struct Pool {
+    uint32_t* w;   // [F_COUNT][NSLOT]
+    __device__ __forceinline__ float getf(int f, int slot) const { return __uint_as_float(w[f * NSLOT + slot]); }
+    __device__ __forceinline__ int geti(int f, int slot) const { return (int)w[f * NSLOT + slot]; }
+    __device__ __forceinline__ void setf(int f, int slot, float v) { w[f * NSLOT + slot] = __float_as_uint(v); }
+    __device__ __forceinline__ void seti(int f, int slot, int v) { w[f * NSLOT + slot] = (uint32_t)v; }
+};
+
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void load_march(const Pool<NSLOT>& pool, int slot, MarchState& m)
 {
-    const int lane = threadIdx.x & 31;
+    m.ro = V3(pool.getf(F_ROX, slot), pool.getf(F_ROY, slot), pool.getf(F_ROZ, slot));
+    m.rd = V3(pool.getf(F_RDX, slot), pool.getf(F_RDY, slot), pool.getf(F_RDZ, slot));
+    m.t = pool.getf(F_T, slot);
+    m.steps = pool.geti(F_STEPS, slot);
+    m.idx = pool.geti(F_IDX, slot);
+    m.t_eval = pool.getf(F_TEVAL, slot);
+    if (VAR::MARCHER != MARCH_PLAIN) {
+        m.w = pool.getf(F_W, slot); m.s = pool.getf(F_S, slot); m.d = pool.getf(F_D, slot);
+    } else {
+        m.w = 1.0f; m.s = 0.0f; m.d = 0.0f;
+    }
+}
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void store_march(Pool<NSLOT>& pool, int slot, const MarchState& m, bool with_ray)
+{
+    if (with_ray || VAR::MARCHER == MARCH_SRC) {
+        pool.setf(F_ROX, slot, m.ro.x); pool.setf(F_ROY, slot, m.ro.y); pool.setf(F_ROZ, slot, m.ro.z);
+    }
+    if (with_ray) {
+        pool.setf(F_RDX, slot, m.rd.x); pool.setf(F_RDY, slot, m.rd.y); pool.setf(F_RDZ, slot, m.rd.z);
+    }
+    pool.setf(F_T, slot, m.t);
+    pool.seti(F_STEPS, slot, m.steps);
+    pool.seti(F_IDX, slot, m.idx);
+    pool.setf(F_TEVAL, slot, m.t_eval);
+    if (VAR::MARCHER != MARCH_PLAIN) {
+        pool.setf(F_W, slot, m.w); pool.setf(F_S, slot, m.s); pool.setf(F_D, slot, m.d);
+    }
+}
+
+template <class VAR, int NSLOT>
+__global__ void __launch_bounds__(kPoolBlock, kPoolMinBlocks) k_pathtrace_pool(const __grid_constant__ KParams P)
+{
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lane_lt = (1u << lane) - 1u;
+    constexpr int kWarpWords = F_COUNT * NSLOT + 2 * (NSLOT / 4);
+    Pool<NSLOT> pool;
+    pool.w = smem + warp * kWarpWords;
+    uint8_t* ready = reinterpret_cast<uint8_t*>(pool.w + F_COUNT * NSLOT);
+    uint8_t* pend = ready + NSLOT;
+    int n_ready = 0, n_pend = NSLOT;          // warp-uniform
 
-    int mode = M_FETCH;
-    PathState st;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t pixel = 0;
-    int pi = 0, pj = 0, s = 0;
+    for (int s = lane; s < NSLOT; s += 32) {
+        pool.seti(F_STATUS, s, ST_FETCH);
+        pend[s] = (uint8_t)s;
+    }
+    __syncwarp();
 
-    unsigned long long c_evals = 0, c_rays = 0, c_normals = 0, c_samples = 0;   // per lane
-    unsigned long long c_iters = 0, c_active = 0, c_rounds = 0;                 // per warp
+    int my = -1;
+    MarchState m;
+    m.ro = m.rd = V3(0.f); m.t = m.w = m.s = m.d = m.t_eval = 0.f; m.steps = m.idx = 0;
+    WorkCounters cnt = { 0, 0, 0, 0 };
+    unsigned long long c_iters = 0, c_active = 0, c_rounds = 0, c_resolved = 0;
 
     for (;;) {
-        const unsigned m_march = __ballot_sync(kFull, mode == M_MARCH);
-        const unsigned m_pend = __ballot_sync(kFull, mode != M_MARCH && mode != M_IDLE);
-        if ((m_march | m_pend) == 0u) break;
-        const int n_march = __popc(m_march), n_pend = __popc(m_pend);
+        // ---------------------------------------------------------------- acquire ready slots
+        const unsigned needy = __ballot_sync(kFull, my < 0);
+        if (needy != 0u && n_ready > 0) {
+            const int r = __popc(needy & lane_lt);
+            if (my < 0 && r < n_ready) {
+                my = ready[n_ready - 1 - r];
+                load_march<VAR, NSLOT>(pool, my, m);
+            }
+            n_ready -= min(__popc(needy), n_ready);
+        }
+        const unsigned active = __ballot_sync(kFull, my >= 0);
 
-        if (n_pend > 0 && (n_march == 0 || n_pend * 32 >= (n_pend + n_march) * P.resolve_q)) {
-            // ------------------------------------------------------------ resolve round
+        // ---------------------------------------------------------------- resolve phase
+        if (active != kFull && n_pend > 0 && (n_pend >= P.resolve_min || active == 0u)) {
             if (VAR::COUNT) c_rounds++;
-            if (mode == M_HIT) {
-                if (VAR::COUNT) c_normals++;
-                if (shade<VAR>(P, st) && begin_bounce<VAR>(P, pixel, P.sample_base + (uint32_t)s, st))
-                    mode = M_MARCH;
-                else
-                    mode = M_DONE;
+            if (my >= 0) {   // park: the slot stays ready-to-march
+                store_march<VAR, NSLOT>(pool, my, m, false);
+                ready[n_ready + __popc(active & lane_lt)] = (uint8_t)my;
+                my = -1;
             }
-            if (mode == M_DONE) {
-                acc.x += st.col.x; acc.y += st.col.y; acc.z += st.col.z; acc.w += 1.0f;
-                if (++s == P.spp) {
-                    P.image_buffer[pixel] = acc;
-                    mode = M_FETCH;
-                } else {
-                    mode = M_NEWPATH;
+            n_ready += __popc(active);
+            __syncwarp();
+            while (n_pend > 0) {
+                const int take = min(n_pend, 32);
+                const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
+                n_pend -= take;
+                if (VAR::COUNT) c_resolved += (unsigned long long)take;
+
+                // ---- load the slot
+                Path p;
+                int st = ST_NONE, samp = 0, k = 0;
+                uint32_t pixel = 0;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                p.m = m;
+                p.col = V3(0.f);
+                p.depth = 0;
+                p.rng = rng_make(0u, 0u, 0u);
+                if (slot >= 0) {
+                    st = pool.geti(F_STATUS, slot);
+                    load_march<VAR, NSLOT>(pool, slot, p.m);
+                    p.col = V3(pool.getf(F_COLX, slot), pool.getf(F_COLY, slot), pool.getf(F_COLZ, slot));
+                    p.depth = pool.geti(F_DEPTH, slot);
+                    pixel = (uint32_t)pool.geti(F_PIXEL, slot);
+                    samp = pool.geti(F_SAMP, slot);
+                    k = pool.geti(F_K, slot);
+                    p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, (uint32_t)pool.geti(F_RNGN, slot));
+                    acc = make_float4(pool.getf(F_ACCX, slot), pool.getf(F_ACCY, slot), pool.getf(F_ACCZ, slot),
+                                      pool.getf(F_ACCW, slot));
                 }
-            }
-            // warp-aggregated pull from the global work queue (tile padding is skipped)
-            for (;;) {
-                const unsigned m_fetch = __ballot_sync(kFull, mode == M_FETCH);
-                if (m_fetch == 0u) break;
-                const int leader = __ffs(m_fetch) - 1;
-                unsigned base = 0;
-                if (lane == leader) base = atomicAdd(P.work_counter, (unsigned)__popc(m_fetch));
-                base = __shfl_sync(kFull, base, leader);
-                if (mode == M_FETCH) {
-                    const unsigned w = base + (unsigned)__popc(m_fetch & lane_lt);
-                    if (w >= P.total_work) {
-                        mode = M_IDLE;
-                    } else if (work_to_pixel(P, w, pi, pj)) {
-                        pixel = (uint32_t)(pi * P.height + pj);
-                        acc = P.image_buffer[pixel];
-                        s = 0;
-                        mode = M_NEWPATH;
+                int pi = (int)(pixel / (uint32_t)P.height), pj = (int)(pixel - (uint32_t)pi * (uint32_t)P.height);
+
+                // ---- run the slot's state machine until it needs marching again (or dies)
+                if (VAR::FAMILY == FAMILY_C) {
+                    if (st == ST_HIT || st == ST_MISS) {
+                        c_after_march<VAR>(P, p, st == ST_HIT ? MARCH_HIT : MARCH_MISS, VAR::COUNT ? &cnt : nullptr);
+                        k++;
+                        st = ST_ADVANCE;
+                    }
+                } else {
+                    if (st == ST_HIT) {
+                        if (VAR::COUNT) { cnt.normals++; cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                        st = (on_hit<VAR>(P, p) && begin_bounce<VAR>(P, p)) ? ST_READY : ST_DONE;
+                    } else if (st == ST_MISS) {
+                        if (VAR::COUNT) { cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                        on_miss<VAR>(P, p);
+                        st = ST_DONE;
                     }
                 }
+                for (;;) {
+                    if (VAR::FAMILY == FAMILY_C) {
+                        if (st == ST_ADVANCE) {
+                            TaskC task; task.launch = samp; task.k = k;
+                            if (c_advance<VAR>(P, pi, pj, p, task, acc, VAR::COUNT ? &cnt : nullptr)) {
+                                st = ST_READY;
+                                k = task.k;
+                            } else if (++samp == P.spp) {      // all reference launches replayed: persist the ray
+                                store_ray(P.ray_buffer + (size_t)pixel * 10, p);
+                                P.image_buffer[pixel] = acc;
+                                st = ST_FETCH;
+                            } else {
+                                p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, 0u);
+                                k = 0;
+                            }
+                        }
+                    } else if (st == ST_DONE) {
+                        acc.x += p.col.x; acc.y += p.col.y; acc.z += p.col.z; acc.w += 1.0f;
+                        if (++samp == P.spp) {
+                            P.image_buffer[pixel] = acc;
+                            st = ST_FETCH;
+                        } else {
+                            st = ST_NEWPATH;
+                        }
+                    }
+                    // warp-aggregated pull from the global work queue (tile padding is skipped)
+                    for (;;) {
+                        const unsigned m_fetch = __ballot_sync(kFull, st == ST_FETCH);
+                        if (m_fetch == 0u) break;
+                        const int leader = __ffs(m_fetch) - 1;
+                        unsigned base = 0;
+                        if (lane == leader) base = atomicAdd(P.work_counter, (unsigned)__popc(m_fetch));
+                        base = __shfl_sync(kFull, base, leader);
+                        if (st == ST_FETCH) {
+                            const unsigned wk = base + (unsigned)__popc(m_fetch & lane_lt);
+                            if (wk >= P.total_work) {
+                                st = ST_DEAD;
+                            } else if (work_to_pixel(P, wk, pi, pj)) {
+                                pixel = (uint32_t)(pi * P.height + pj);
+                                acc = P.image_buffer[pixel];
+                                samp = 0;
+                                k = 0;
+                                if (VAR::FAMILY == FAMILY_C) {
+                                    load_ray(P.ray_buffer + (size_t)pixel * 10, p);
+                                    p.rng = rng_make(pixel, P.sample_base, 0u);
+                                    st = ST_ADVANCE;
+                                } else {
+                                    st = ST_NEWPATH;
+                                }
+                            }
+                        }
+                    }
+                    if (VAR::FAMILY != FAMILY_C && st == ST_NEWPATH) {
+                        if (VAR::COUNT) cnt.samples++;
+                        begin_path<VAR>(P, pixel, pi, pj, P.sample_base + (uint32_t)samp, p);
+                        st = begin_bounce<VAR>(P, p) ? ST_READY : ST_DONE;
+                    }
+                    const bool more = VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE);
+                    if (__ballot_sync(kFull, more) == 0u) break;
+                }
+
+                // ---- write the slot back; ready slots go on the ready stack
+                if (slot >= 0) {
+                    pool.seti(F_STATUS, slot, st);
+                    if (st == ST_READY) {
+                        store_march<VAR, NSLOT>(pool, slot, p.m, true);
+                        pool.setf(F_COLX, slot, p.col.x); pool.setf(F_COLY, slot, p.col.y); pool.setf(F_COLZ, slot, p.col.z);
+                        pool.seti(F_DEPTH, slot, p.depth);
+                        pool.seti(F_PIXEL, slot, (int)pixel);
+                        pool.seti(F_SAMP, slot, samp);
+                        pool.seti(F_K, slot, k);
+                        pool.seti(F_RNGN, slot, (int)p.rng.n);
+                        pool.setf(F_ACCX, slot, acc.x); pool.setf(F_ACCY, slot, acc.y);
+                        pool.setf(F_ACCZ, slot, acc.z); pool.setf(F_ACCW, slot, acc.w);
+                    }
+                }
+                const unsigned rdy = __ballot_sync(kFull, slot >= 0 && st == ST_READY);
+                if (slot >= 0 && st == ST_READY) ready[n_ready + __popc(rdy & lane_lt)] = (uint8_t)slot;
+                n_ready += __popc(rdy);
+                __syncwarp();
             }
-            if (mode == M_NEWPATH) {
-                if (VAR::COUNT) c_samples++;
-                begin_path<VAR>(P, pixel, pi, pj, P.sample_base + (uint32_t)s, st);
-                mode = begin_bounce<VAR>(P, pixel, P.sample_base + (uint32_t)s, st) ? M_MARCH : M_DONE;
-            }
+            continue;
         }
+        if (active == 0u) break;   // nothing marching, nothing pending, nothing ready: pool drained
 
         // ---------------------------------------------------------------- march step
-        if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(__ballot_sync(kFull, mode == M_MARCH)); }
-        if (mode == M_MARCH) {
-            const int status = march_step<VAR>(P, st);
-            if (VAR::COUNT) c_evals++;
+        if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(active); }
+        int status = MARCH_CONTINUE;
+        if (my >= 0) status = march_step<VAR>(P, m);
+        const unsigned fin = __ballot_sync(kFull, status != MARCH_CONTINUE);
+        if (fin != 0u) {
             if (status != MARCH_CONTINUE) {
-                if (VAR::COUNT) c_rays++;
-                if (status == MARCH_HIT) {
-                    mode = M_HIT;
-                } else {
-                    miss(P, st);
-                    mode = M_DONE;
-                }
+                store_march<VAR, NSLOT>(pool, my, m, false);
+                pool.seti(F_STATUS, my, status == MARCH_HIT ? ST_HIT : ST_MISS);
+                pend[n_pend + __popc(fin & lane_lt)] = (uint8_t)my;
+                my = -1;
             }
+            n_pend += __popc(fin);
+            __syncwarp();
         }
     }
 
     if (VAR::COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            c_evals += __shfl_xor_sync(kFull, c_evals, o);
-            c_rays += __shfl_xor_sync(kFull, c_rays, o);
-            c_normals += __shfl_xor_sync(kFull, c_normals, o);
-            c_samples += __shfl_xor_sync(kFull, c_samples, o);
+            cnt.evals += __shfl_xor_sync(kFull, cnt.evals, o);
+            cnt.rays += __shfl_xor_sync(kFull, cnt.rays, o);
+            cnt.normals += __shfl_xor_sync(kFull, cnt.normals, o);
+            cnt.samples += __shfl_xor_sync(kFull, cnt.samples, o);
         }
         if (lane == 0) {
-            atomicAdd(&P.counters[0], c_evals);
-            atomicAdd(&P.counters[1], c_rays);
-            atomicAdd(&P.counters[2], c_normals);
-            atomicAdd(&P.counters[3], c_samples);
+            atomicAdd(&P.counters[0], cnt.evals);
+            atomicAdd(&P.counters[1], cnt.rays);
+            atomicAdd(&P.counters[2], cnt.normals);
+            atomicAdd(&P.counters[3], cnt.samples);
             atomicAdd(&P.counters[4], c_iters);
             atomicAdd(&P.counters[5], c_active);
             atomicAdd(&P.counters[6], c_rounds);
+            atomicAdd(&P.counters[8], c_resolved);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Simple kernel: one thread per work item, all spp, every path run to completion.
+// Simple kernel: one thread per work item, all samples, every path run to completion.
 // ------------------------------------------------------------------------------------------
 template <class VAR>
 __global__ void __launch_bounds__(kSimpleBlock) k_pathtrace_simple(const __grid_constant__ KParams P)
@@ -148,18 +316,30 @@ __global__ void __launch_bounds__(kSimpleBlock) k_pathtrace_simple(const __grid_
     if (w >= P.total_work || !work_to_pixel(P, w, i, j)) return;
     const uint32_t pixel = (uint32_t)(i * P.height + j);
     float4 acc = P.image_buffer[pixel];
-    unsigned long long cnt[4] = { 0, 0, 0, 0 };
-    for (int s = 0; s < P.spp; ++s) {
-        vec3 c = trace_sample<VAR>(P, pixel, i, j, P.sample_base + (uint32_t)s, cnt);
-        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += 1.0f;
+    WorkCounters cnt = { 0, 0, 0, 0 };
+    if (VAR::FAMILY == FAMILY_C) {
+        trace_pixel_c<VAR>(P, pixel, i, j, acc, VAR::COUNT ? &cnt : nullptr);
+    } else {
+        for (int s = 0; s < P.spp; ++s) {
+            vec3 c = trace_sample<VAR>(P, pixel, i, j, P.sample_base + (uint32_t)s, VAR::COUNT ? &cnt : nullptr);
+            acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += 1.0f;
+        }
     }
     P.image_buffer[pixel] = acc;
     if (VAR::COUNT) {
-        atomicAdd(&P.counters[0], cnt[0]);
-        atomicAdd(&P.counters[1], cnt[1]);
-        atomicAdd(&P.counters[2], cnt[2]);
-        atomicAdd(&P.counters[3], cnt[3]);
+        atomicAdd(&P.counters[0], cnt.evals);
+        atomicAdd(&P.counters[1], cnt.rays);
+        atomicAdd(&P.counters[2], cnt.normals);
+        atomicAdd(&P.counters[3], cnt.samples);
     }
+}
+
+// refresh() of src/renderer.py:12-22: the accumulators are cleared by a memset; the ray buffer keeps
+// origin / direction / colour and only has `depth` reset (the reference does not reset the colour).
+__global__ void __launch_bounds__(256) k_refresh_depth(float* ray_buffer, int n)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) reinterpret_cast<int*>(ray_buffer)[(size_t)p * 10 + 9] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -228,10 +408,20 @@ __global__ void __launch_bounds__(256) k_post_process(const float4* __restrict__
 // ------------------------------------------------------------------------------------------
 // Host-side launchers (called from capi.cu)
 // ------------------------------------------------------------------------------------------
+template <int NSLOT>
+constexpr size_t pool_smem_bytes() { return (size_t)(kPoolBlock / 32) * (F_COUNT * NSLOT + 2 * (NSLOT / 4)) * sizeof(uint32_t); }
+
 template <class VAR>
-static cudaError_t launch_persistent_t(const KParams& P, int grid, cudaStream_t stream)
+static cudaError_t launch_pool_t(const KParams& P, int grid, cudaStream_t stream)
 {
-    k_pathtrace_persistent<VAR><<<grid, kPersistentBlock, 0, stream>>>(P);
+    constexpr size_t smem = pool_smem_bytes<kPoolSlots>();
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_pathtrace_pool<VAR, kPoolSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_pathtrace_pool<VAR, kPoolSlots><<<grid, kPoolBlock, smem, stream>>>(P);
     return cudaGetLastError();
 }
 template <class VAR>
@@ -241,38 +431,62 @@ static cudaError_t launch_simple_t(const KParams& P, cudaStream_t stream)
     k_pathtrace_simple<VAR><<<grid, kSimpleBlock, 0, stream>>>(P);
     return cudaGetLastError();
 }
-
 template <class VAR>
 static cudaError_t occupancy_t(int* blocks_per_sm)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_pathtrace_persistent<VAR>, kPersistentBlock, 0);
+    constexpr size_t smem = pool_smem_bytes<kPoolSlots>();
+    cudaError_t e = cudaFuncSetAttribute(k_pathtrace_pool<VAR, kPoolSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_pathtrace_pool<VAR, kPoolSlots>, kPoolBlock, smem);
 }
 
-// Dispatch on (family, object count, count_work).  Family A scenes are boxes only.
+// Dispatch on (family, marcher, shape set, object count, count_work).
+#define RT_CASE(FN, FAM, NOBJ, SHAPES, MARCH, ...)                                                   \
+    do {                                                                                             \
+        if (sel.count) return FN<Variant<FAM, NOBJ, SHAPES, MARCH, true>>(__VA_ARGS__);              \
+        return FN<Variant<FAM, NOBJ, SHAPES, MARCH, false>>(__VA_ARGS__);                            \
+    } while (0)
+
 #define RT_DISPATCH(FN, ...)                                                                         \
     do {                                                                                             \
-        if (sel.family == FAMILY_A) {                                                                \
-            if (sel.nobj == 8) {                                                                     \
-                if (sel.count) return FN<Variant<FAMILY_A, 8, true, true>>(__VA_ARGS__);             \
-                return FN<Variant<FAMILY_A, 8, true, false>>(__VA_ARGS__);                           \
-            }                                                                                        \
-            if (sel.count) return FN<Variant<FAMILY_A, 0, true, true>>(__VA_ARGS__);                 \
-            return FN<Variant<FAMILY_A, 0, true, false>>(__VA_ARGS__);                               \
+        if (sel.family == FAMILY_A && sel.marcher == MARCH_PLAIN && !sel.bunny) {                    \
+            if (sel.nobj == 8) RT_CASE(FN, FAMILY_A, 8, SHAPESET_BOX, MARCH_PLAIN, __VA_ARGS__);     \
+            RT_CASE(FN, FAMILY_A, 0, SHAPESET_BOX, MARCH_PLAIN, __VA_ARGS__);                        \
         }                                                                                            \
+        if (sel.family == FAMILY_B && sel.marcher == MARCH_PLAIN && !sel.bunny)                      \
+            RT_CASE(FN, FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_PLAIN, __VA_ARGS__);                   \
+        if (sel.family == FAMILY_B && sel.marcher == MARCH_ENHANCED && !sel.bunny)                   \
+            RT_CASE(FN, FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_ENHANCED, __VA_ARGS__);                \
+        if (sel.family == FAMILY_B && sel.marcher == MARCH_ENHANCED && sel.bunny)                    \
+            RT_CASE(FN, FAMILY_B, 0, SHAPESET_BUNNY, MARCH_ENHANCED, __VA_ARGS__);                   \
+        if (sel.family == FAMILY_C && sel.marcher == MARCH_SRC && !sel.bunny)                        \
+            RT_CASE(FN, FAMILY_C, 0, SHAPESET_ANALYTIC, MARCH_SRC, __VA_ARGS__);                     \
         return cudaErrorNotSupported;                                                                \
     } while (0)
 
-cudaError_t launch_pathtrace_persistent(const KernelSelect& sel, const KParams& P, int grid, cudaStream_t stream)
+cudaError_t launch_pathtrace_pool(const KernelSelect& sel, const KParams& P, int grid, cudaStream_t stream)
 {
-    RT_DISPATCH(launch_persistent_t, P, grid, stream);
+    RT_DISPATCH(launch_pool_t, P, grid, stream);
 }
 cudaError_t launch_pathtrace_simple(const KernelSelect& sel, const KParams& P, cudaStream_t stream)
 {
     RT_DISPATCH(launch_simple_t, P, stream);
 }
-cudaError_t persistent_occupancy(const KernelSelect& sel, int* blocks_per_sm)
+cudaError_t pool_occupancy(const KernelSelect& sel, int* blocks_per_sm)
 {
     RT_DISPATCH(occupancy_t, blocks_per_sm);
+}
+bool kernel_supported(const KernelSelect& sel)
+{
+    if (sel.family == FAMILY_A) return sel.marcher == MARCH_PLAIN && !sel.bunny;
+    if (sel.family == FAMILY_B) return (sel.marcher == MARCH_PLAIN && !sel.bunny) || sel.marcher == MARCH_ENHANCED;
+    if (sel.family == FAMILY_C) return sel.marcher == MARCH_SRC && !sel.bunny;
+    return false;
+}
+cudaError_t launch_refresh_depth(float* ray_buffer, int n, cudaStream_t stream)
+{
+    k_refresh_depth<<<(n + 255) / 256, 256, 0, stream>>>(ray_buffer, n);
+    return cudaGetLastError();
 }
 cudaError_t launch_post_process(const float4* image_buffer, float* image_pixels, int n, int mode, float exposure,
                                 float inv_gamma, cudaStream_t stream)

@@ -6,19 +6,24 @@
 
 namespace rt {
 
-constexpr int kPersistentBlock = 256;      // 8 warps per CTA
-constexpr int kPersistentMinBlocks = 4;    // <= 64 registers/thread -> 32 warps per SM
+constexpr int kPoolBlock = 256;        // 8 warps per CTA
+constexpr int kPoolMinBlocks = 4;      // <= 64 registers/thread -> 32 warps per SM
+constexpr int kPoolSlots = 64;         // path slots per warp: 32 marching + 32 ready / pending
 constexpr int kSimpleBlock = 128;
 
 struct KernelSelect {
     int family;
+    int marcher;
     int nobj;
+    bool bunny;
     bool count;
 };
 
-cudaError_t launch_pathtrace_persistent(const KernelSelect& sel, const KParams& P, int grid, cudaStream_t stream);
+bool kernel_supported(const KernelSelect& sel);
+cudaError_t launch_pathtrace_pool(const KernelSelect& sel, const KParams& P, int grid, cudaStream_t stream);
 cudaError_t launch_pathtrace_simple(const KernelSelect& sel, const KParams& P, cudaStream_t stream);
-cudaError_t persistent_occupancy(const KernelSelect& sel, int* blocks_per_sm);
+cudaError_t pool_occupancy(const KernelSelect& sel, int* blocks_per_sm);
+cudaError_t launch_refresh_depth(float* ray_buffer, int n, cudaStream_t stream);
 cudaError_t launch_post_process(const float4* image_buffer, float* image_pixels, int n, int mode, float exposure,
                                 float inv_gamma, cudaStream_t stream);
 

@@ -7,8 +7,8 @@ namespace rt {
 
 constexpr int kMaxObjects = 16;
 
-// Hot geometry of one SDF object: 16 words.  `m` is Transform.matrix (src/dataclass.py:28),
-// derived on the host by rtpbr_set_scene.
+// Hot geometry of one SDF object: 16 words, 16-byte aligned so it loads as 4 x 128 bit.
+// `m` is Transform.matrix (src/dataclass.py:28), derived on the host by rtpbr_set_scene.
 struct alignas(16) DevGeom {
     float px, py, pz;
     float m[9];
@@ -37,8 +37,8 @@ struct DevCamera {
 
 struct KParams {
     int32_t width, height;
-    int32_t spp;
-    uint32_t sample_base;
+    int32_t spp;             // families A/B: samples per pixel in this launch; family C: reference launches
+    uint32_t sample_base;    // launch index of the first sample (Philox counter word 1)
     uint32_t seed;
     int32_t max_bounces, max_steps;
     float t_start, hit_eps, t_far;
@@ -46,25 +46,30 @@ struct KParams {
     int32_t relax_guard, relax_reset;
     float normal_h, box_round;
     float visibility_min, visibility_max;
-    int32_t f0_variant;
+    int32_t bsdf, f0_variant;
     int32_t sky;
     float sky_scale;
     float min_dis, pixel_radius, quality_per_sample;
+    float inv_max_bounces;   // float(1.0 / MAX_RAYTRACE), src/pathtracer.py:68
     int32_t black_background;
+    int32_t nearest_seed, normal_mode, samples_per_pixel;
     int32_t frame;
+    float anim_m[9];         // bunny programmatic animation: angle(vec3(0, 0, t)), bunny_sdf_glass.py:214
+    float anim_bob;          // 0.1 * sin(t), :215
     // shard: this context renders global columns i with (i / band) % nranks == rank
     int32_t rank, nranks, band;
     int32_t local_cols;      // number of columns owned by this rank
     uint32_t total_work;     // work items (pixels incl. tile padding) on this rank
     int32_t tiles_per_col;   // ceil(H / 8)
     int32_t nobj;
-    int32_t resolve_q;       // resolve round when pending * 32 >= live * resolve_q
+    int32_t resolve_min;     // pool kernel: resolve when this many slots are pending (or lanes would idle)
     DevCamera cam;
     DevGeom geom[kMaxObjects];
     DevMaterial mat[kMaxObjects];
     // device pointers
     float4* image_buffer;           // (W,H) vec4, j fastest
-    const float* rr_prob;           // [max_bounces] Russian-roulette table
+    float* ray_buffer;              // family C: (W,H,10) AOS Ray, src/fileds.py:7
+    const float* rr_prob;           // [max_bounces] Russian-roulette table (families A/B)
     const float* env;               // (env_w, env_h, 3) or nullptr
     int32_t env_w, env_h;
     unsigned int* work_counter;     // persistent-kernel work queue head

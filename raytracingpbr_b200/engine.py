@@ -34,6 +34,7 @@ class PathTracer:
         self.tonemap = tonemap or dict(mode=2, exposure=1.0, gamma=2.2)
         self.image_buffer = Field(self.ctx, N.BUF_IMAGE_BUFFER, 4)     # src/fileds.py:8
         self.image_pixels = Field(self.ctx, N.BUF_IMAGE_PIXELS, 3)     # src/fileds.py:9
+        self.ray_buffer = Field(self.ctx, N.BUF_RAY_BUFFER, 10)        # src/fileds.py:7 (family C only)
         self.set_scene(objects)
         self.set_camera(camera)
 
@@ -45,6 +46,10 @@ class PathTracer:
     def set_camera(self, camera: Camera) -> None:
         self.camera = camera
         self.ctx.set_camera(camera.to_native() if isinstance(camera, Camera) else camera)
+
+    def set_envmap(self, table: np.ndarray) -> None:
+        """Processed environment table, (w, h, 3) f32 (see raytracingpbr_b200.ibl)."""
+        self.ctx.set_envmap(table)
 
     # frame loop --------------------------------------------------------------------------
     def refresh(self) -> None:

@@ -67,6 +67,12 @@ def hostcheck() -> C.CDLL:
     L.hostcheck_pathtrace.restype = C.c_int
     L.hostcheck_pathtrace.argtypes = [C.POINTER(N.RtpbrConfig), C.POINTER(N.RtpbrCamera), C.POINTER(N.RtpbrObject), C.c_int,
                                       C.POINTER(C.c_float), C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    L.hostcheck_pathtrace_ex.restype = C.c_int
+    f32p = C.POINTER(C.c_float)
+    L.hostcheck_pathtrace_ex.argtypes = [C.POINTER(N.RtpbrConfig), C.POINTER(N.RtpbrCamera), C.POINTER(N.RtpbrObject), C.c_int,
+                                         f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    L.hostcheck_sd_bunny.restype = C.c_float
+    L.hostcheck_sd_bunny.argtypes = [f32p]
     L.hostcheck_sincos.restype = None
     L.hostcheck_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.hostcheck_atan2.restype = C.c_float
@@ -79,15 +85,20 @@ def hostcheck() -> C.CDLL:
     return L
 
 
-def hostcheck_pathtrace(cfg, camera, objects, spp, sample_base=0, image=None, rank=0, nranks=1, band=32):
+def hostcheck_pathtrace(cfg, camera, objects, spp, sample_base=0, image=None, rank=0, nranks=1, band=32,
+                        ray_buffer=None, env=None, frame=0):
     L = hostcheck()
     nobjs = [o.to_native() if isinstance(o, SDFObject) else o for o in objects]
     arr = (N.RtpbrObject * len(nobjs))(*nobjs)
     cam = camera.to_native() if isinstance(camera, Camera) else camera
     if image is None:
         image = np.zeros((cfg.width, cfg.height, 4), dtype=np.float32)
-    rc = L.hostcheck_pathtrace(C.byref(cfg), C.byref(cam), arr, len(nobjs), image.ctypes.data_as(C.POINTER(C.c_float)),
-                               spp, sample_base, rank, nranks, band)
+    f32p = C.POINTER(C.c_float)
+    rc = L.hostcheck_pathtrace_ex(C.byref(cfg), C.byref(cam), arr, len(nobjs), image.ctypes.data_as(f32p),
+                                  ray_buffer.ctypes.data_as(f32p) if ray_buffer is not None else None,
+                                  env.ctypes.data_as(f32p) if env is not None else None,
+                                  env.shape[0] if env is not None else 0, env.shape[1] if env is not None else 0,
+                                  frame, spp, sample_base, rank, nranks, band)
     assert rc == 0, rc
     return image
 

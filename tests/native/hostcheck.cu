@@ -1,7 +1,8 @@
 // hostcheck.cu -- TEST HARNESS ONLY.  Runs the product's __host__ __device__ path-tracing
 // building blocks (raytracingpbr_b200/csrc/rt_integrator.cuh) on the CPU so that their fp32
-// operation sequence can be compared bit-for-bit with the independent C oracle on a machine
-// without a GPU.  Not linked into librtpbr.so and not reachable from the product API.
+// operation sequence can be compared bit-for-bit with the independent C oracle and the golden
+// fixtures on a machine without a GPU.  Not linked into librtpbr.so and not reachable from the
+// product API.
 #include <cstring>
 #include <vector>
 
@@ -11,43 +12,66 @@
 
 using namespace rt;
 
-extern "C" __attribute__((visibility("default"))) int hostcheck_pathtrace(const RtpbrConfig* cfg, const RtpbrCamera* cam,
-                                                                          const RtpbrObject* objs, int n, float* image_buffer,
-                                                                          int spp, uint32_t sample_base, int rank, int nranks,
-                                                                          int band)
+#define HC_API extern "C" __attribute__((visibility("default")))
+
+template <class VAR>
+static void run(const KParams& P, float4* buf)
 {
-    if (cfg->family != RTPBR_FAMILY_A) return RTPBR_ERR_UNSUPPORTED;
-    KParams P;
-    memset(&P, 0, sizeof(P));
-    fill_config(P, *cfg);
-    fill_shard(P, rank, nranks, band);
-    fill_objects(P, objs, n);
-    fill_camera(P, *cfg, *cam);
-    std::vector<float> rr = rr_table(*cfg);
-    P.rr_prob = rr.data();
-    P.spp = spp;
-    P.sample_base = sample_base;
-    float4* buf = reinterpret_cast<float4*>(image_buffer);
-    typedef Variant<FAMILY_A, 0, true, false> VAR;
 #pragma omp parallel for schedule(dynamic, 64)
     for (long long w = 0; w < (long long)P.total_work; ++w) {
         int i, j;
         if (!work_to_pixel(P, (uint32_t)w, i, j)) continue;
         const uint32_t pixel = (uint32_t)(i * P.height + j);
         float4 acc = buf[pixel];
-        for (int s = 0; s < spp; ++s) {
-            vec3 c = trace_sample<VAR>(P, pixel, i, j, sample_base + (uint32_t)s, nullptr);
-            acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += 1.0f;
+        if (VAR::FAMILY == FAMILY_C) {
+            trace_pixel_c<VAR>(P, pixel, i, j, acc, nullptr);
+        } else {
+            for (int s = 0; s < P.spp; ++s) {
+                vec3 c = trace_sample<VAR>(P, pixel, i, j, P.sample_base + (uint32_t)s, nullptr);
+                acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += 1.0f;
+            }
         }
         buf[pixel] = acc;
     }
+}
+
+HC_API int hostcheck_pathtrace_ex(const RtpbrConfig* cfg, const RtpbrCamera* cam, const RtpbrObject* objs, int n,
+                                  float* image_buffer, float* ray_buffer, const float* env, int env_w, int env_h, int frame,
+                                  int spp, uint32_t sample_base, int rank, int nranks, int band)
+{
+    KParams P;
+    memset(&P, 0, sizeof(P));
+    fill_config(P, *cfg);
+    fill_shard(P, rank, nranks, band);
+    fill_objects(P, objs, n);
+    fill_camera(P, *cfg, *cam);
+    fill_frame(P, frame);
+    std::vector<float> rr = rr_table(*cfg);
+    P.rr_prob = rr.data();
+    P.spp = spp;
+    P.sample_base = sample_base;
+    P.env = env; P.env_w = env_w; P.env_h = env_h;
+    P.ray_buffer = ray_buffer;
+    float4* buf = reinterpret_cast<float4*>(image_buffer);
+    bool bunny = false;
+    for (int k = 0; k < n; ++k) bunny = bunny || objs[k].type == RTPBR_SHAPE_BUNNY;
+    if (cfg->family == RTPBR_FAMILY_A) run<Variant<FAMILY_A, 0, SHAPESET_BOX, MARCH_PLAIN, false>>(P, buf);
+    else if (cfg->family == RTPBR_FAMILY_B && cfg->marcher == RTPBR_MARCH_PLAIN) run<Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_PLAIN, false>>(P, buf);
+    else if (cfg->family == RTPBR_FAMILY_B && bunny) run<Variant<FAMILY_B, 0, SHAPESET_BUNNY, MARCH_ENHANCED, false>>(P, buf);
+    else if (cfg->family == RTPBR_FAMILY_B) run<Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_ENHANCED, false>>(P, buf);
+    else if (cfg->family == RTPBR_FAMILY_C && ray_buffer) run<Variant<FAMILY_C, 0, SHAPESET_ANALYTIC, MARCH_SRC, false>>(P, buf);
+    else return RTPBR_ERR_UNSUPPORTED;
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) void hostcheck_sincos(float x, float* s, float* c) { sincos_rt(x, *s, *c); }
-extern "C" __attribute__((visibility("default"))) float hostcheck_atan2(float y, float x) { return atan2_rt(y, x); }
-extern "C" __attribute__((visibility("default"))) float hostcheck_asin(float x) { return asin_rt(x); }
-extern "C" __attribute__((visibility("default"))) void hostcheck_euler(const float rot_deg[3], float out9[9])
+HC_API int hostcheck_pathtrace(const RtpbrConfig* cfg, const RtpbrCamera* cam, const RtpbrObject* objs, int n, float* image_buffer,
+                               int spp, uint32_t sample_base, int rank, int nranks, int band)
 {
-    euler_matrix_deg(rot_deg, out9);
+    return hostcheck_pathtrace_ex(cfg, cam, objs, n, image_buffer, nullptr, nullptr, 0, 0, 0, spp, sample_base, rank, nranks, band);
 }
+
+HC_API void hostcheck_sincos(float x, float* s, float* c) { sincos_rt(x, *s, *c); }
+HC_API float hostcheck_atan2(float y, float x) { return atan2_rt(y, x); }
+HC_API float hostcheck_asin(float x) { return asin_rt(x); }
+HC_API void hostcheck_euler(const float rot_deg[3], float out9[9]) { euler_matrix_deg(rot_deg, out9); }
+HC_API float hostcheck_sd_bunny(const float p[3]) { return sd_bunny(V3(p[0], p[1], p[2])); }

@@ -149,6 +149,30 @@ def test_oracle_family_c_matches_reference_source():
     assert img[..., 3].sum() > 0 and (g["ray_buffer"][..., 9].view(np.int32) < 0).any()
 
 
+@pytest.mark.parametrize("name", FAMILY_B + ["src_scene"])
+def test_product_host_code_families_bc_match_reference_source(name):
+    # the product's __host__ __device__ integrator (rt_integrator.cuh) compiled for the CPU
+    g, cfg, objs, cam, tm, env = common.golden_case(name)
+    frame = int(g["frame"]) if "frame" in g else 0
+    if name == "src_scene":
+        rb = np.zeros((cfg.width, cfg.height, 10), np.float32)
+        img = common.hostcheck_pathtrace(cfg, cam, objs, 1, ray_buffer=rb, env=env)
+        assert np.array_equal(img, g["image_buffer_first"])
+        img = common.hostcheck_pathtrace(cfg, cam, objs, int(g["launches"]) - 1, sample_base=1, image=img, ray_buffer=rb, env=env)
+        assert np.array_equal(img, g["image_buffer"])
+        assert np.array_equal(rb.view(np.int32), g["ray_buffer"].view(np.int32))
+    else:
+        img = common.hostcheck_pathtrace(cfg, cam, objs, int(g["spp"]), env=env, frame=frame)
+        assert np.array_equal(img, g["image_buffer"])
+
+
+def test_product_bunny_sdf_matches_reference_source():
+    g = np.load(os.path.join(GOLDEN, "bunny_glass.npz"))
+    H = common.hostcheck()
+    for p, want in zip(g["bunny_points"], g["bunny_sd"]):
+        assert np.float32(H.hostcheck_sd_bunny(f32p(p))) == want
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", SHORTEST, ids=os.path.basename)
 def test_cuda_image_buffer_matches_reference_source(path):
@@ -167,3 +191,52 @@ def test_cuda_image_buffer_matches_reference_source(path):
         assert np.array_equal(buf, g["image_buffer"])
         # tone mapping uses pow(): tolerance, not bits (shortest:124-129)
         np.testing.assert_allclose(pix, g["image_pixels"], atol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FAMILY_B)
+def test_cuda_family_b_matches_reference_source(name):
+    from raytracingpbr_b200 import PathTracer, _native as N
+    g, cfg, objs, cam, tm, env = common.golden_case(name)
+    for kernel in (N.KERNEL_PERSISTENT, N.KERNEL_SIMPLE):
+        cfg.kernel = kernel
+        with PathTracer(cfg, objs, cam, tm) as pt:
+            if env is not None:
+                pt.set_envmap(env)
+            if "frame" in g:
+                pt.ctx.set_frame(int(g["frame"]))
+            pt.refresh()
+            pt.pathtrace(1)
+            first = pt.image_buffer.to_numpy()
+            if int(g["spp"]) > 1:
+                pt.pathtrace(int(g["spp"]) - 1)
+            buf = pt.image_buffer.to_numpy()
+        assert np.array_equal(first, g["image_buffer_first"]), (name, kernel)
+        assert np.array_equal(buf, g["image_buffer"]), (name, kernel)
+
+
+@pytest.mark.gpu
+def test_cuda_family_c_matches_reference_source():
+    from raytracingpbr_b200 import PathTracer, _native as N
+    g, cfg, objs, cam, tm, env = common.golden_case("src_scene")
+    for kernel in (N.KERNEL_PERSISTENT, N.KERNEL_SIMPLE):
+        cfg.kernel = kernel
+        with PathTracer(cfg, objs, cam, tm) as pt:
+            pt.set_envmap(env)
+            pt.refresh()
+            pt.pathtrace(1)                                  # one reference launch
+            first = pt.image_buffer.to_numpy()
+            for _ in range(int(g["launches"]) - 1):          # launch by launch, like src/renderer.py:29-30
+                pt.pathtrace(1)
+            buf = pt.image_buffer.to_numpy()
+            rb = pt.ray_buffer.to_numpy()
+        assert np.array_equal(first, g["image_buffer_first"]), kernel
+        assert np.array_equal(buf, g["image_buffer"]), kernel
+        assert np.array_equal(rb.view(np.int32), g["ray_buffer"].view(np.int32)), kernel
+        # several reference launches replayed inside ONE kernel launch give the same bits
+        with PathTracer(cfg, objs, cam, tm) as pt:
+            pt.set_envmap(env)
+            pt.refresh()
+            pt.pathtrace(int(g["launches"]))
+            assert np.array_equal(pt.image_buffer.to_numpy(), g["image_buffer"]), kernel
+            assert np.array_equal(pt.ray_buffer.to_numpy().view(np.int32), g["ray_buffer"].view(np.int32)), kernel
