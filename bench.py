@@ -47,7 +47,8 @@ UNIT = "Msamples/s"
 W, H, SPP, BOUNCES = 1024, 1024, 64, 8
 WORKLOAD = "C1: cornell_box_shortest scene, 1024x1024, 64 spp, max 8 bounces"
 # bytes / flops per unit
-BYTES_PER_PIXEL_PER_LAUNCH = 32          # vec4 f32 accumulator: 16 B read + 16 B write
+BYTES_PER_SAMPLE = 16                    # pool kernel: one float4 (radiance, 1) per sample into the scratch buffer
+BYTES_PER_PIXEL_PER_LAUNCH = 32          # simple kernel: vec4 f32 accumulator, 16 B read + 16 B write
 FLOP_PER_SCENE_EVAL = 8 * 41             # 8 boxes x 41 flop
 FLOP_PER_NORMAL = 4 * 41
 FLOP_PER_RAY_SHADE = 150
@@ -289,12 +290,13 @@ def main() -> int:
     hbm_peak, peak_src, sm_max_mhz = peaks()
     k_ms = kernel_ms_max / max(kernel_launches, 1)
     local_pixels = W * H / world
-    alg_bytes = BYTES_PER_PIXEL_PER_LAUNCH * local_pixels
+    alg_bytes = (BYTES_PER_SAMPLE * local_pixels * spp if kernel == N.KERNEL_PERSISTENT
+                 else BYTES_PER_PIXEL_PER_LAUNCH * local_pixels)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "k_pathtrace_pool" if kernel == N.KERNEL_PERSISTENT else "k_pathtrace_simple",
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
             "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "kernel_share_of_step": kernel_ms_max / ms,
-            "note": "this path is FP32-issue bound, not HBM bound (32 B per pixel per launch); see fp32"}
+            "note": "this path is instruction-issue bound, not HBM bound (16 B written per sample); see fp32"}
 
     # counted work (untimed extra pass with the counting variant of the kernel)
     fp32 = None

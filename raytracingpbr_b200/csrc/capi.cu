@@ -84,7 +84,9 @@ struct RtpbrContext {
     float* d_ray_buffer = nullptr;
     float* d_rr = nullptr;
     float* d_env = nullptr;
-    unsigned int* d_work = nullptr;
+    unsigned long long* d_work = nullptr;
+    float4* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
     unsigned long long* d_counters = nullptr;
     void* d_flush = nullptr;
     bool have_scene = false, have_camera = false, has_bunny = false;
@@ -187,7 +189,7 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     const size_t n = npixels(c);
     CREATE_TRY(cudaMalloc(&c->d_image_buffer, n * sizeof(float4)));
     CREATE_TRY(cudaMalloc(&c->d_image_pixels, n * 3 * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&c->d_work, sizeof(unsigned int)));
+    CREATE_TRY(cudaMalloc(&c->d_work, sizeof(unsigned long long)));
     CREATE_TRY(cudaMalloc(&c->d_counters, RTPBR_CNT_COUNT * sizeof(unsigned long long)));
     CREATE_TRY(cudaMemsetAsync(c->d_image_buffer, 0, n * sizeof(float4), c->stream));
     CREATE_TRY(cudaMemsetAsync(c->d_image_pixels, 0, n * 3 * sizeof(float), c->stream));
@@ -227,6 +229,7 @@ int rtpbr_destroy(RtpbrContext* c)
     cudaFree(c->d_rr);
     cudaFree(c->d_env);
     cudaFree(c->d_work);
+    cudaFree(c->d_scratch);
     cudaFree(c->d_counters);
     cudaFree(c->d_flush);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -314,47 +317,96 @@ int rtpbr_refresh(RtpbrContext* c)
     return RTPBR_OK;
 }
 
-int rtpbr_pathtrace(RtpbrContext* c, int spp)
+// Launch sequence of one rtpbr_pathtrace call.
+//   families A/B, pool kernel: the spp are processed in chunks sized so that the per-sample scratch
+//   buffer ([pixel items][chunk] float4) stays within the scratch budget (RTPBR_SCRATCH_MB, default
+//   4096); per chunk: k_pathtrace_pool (work item = one path) then k_fold_samples (ordered sum).
+//   family C / simple kernel: one launch.
+static int launch_pool_chunk(RtpbrContext* c, const rt::KernelSelect& sel, std::pair<cudaEvent_t, cudaEvent_t>& ev,
+                             unsigned long long items)
 {
-    if (!c) return fail(RTPBR_ERR_ARG, "null context");
-    if (spp < 1) return fail(RTPBR_ERR_ARG, "spp must be >= 1");
-    if (!c->have_scene || !c->have_camera) return fail(RTPBR_ERR_STATE, "set_scene and set_camera must precede pathtrace");
-    CUDA_TRY(cudaSetDevice(c->device));
-    c->P.spp = spp;
-    c->P.sample_base = c->sample_base;
-    const rt::KernelSelect sel = select_kernel(c);
+    if (c->blocks_per_sm == 0) {
+        CUDA_TRY(rt::pool_occupancy(sel, &c->blocks_per_sm));
+        if (c->blocks_per_sm < 1) return fail(RTPBR_ERR_CUDA, "pool kernel does not fit on an SM");
+    }
+    long long grid = (long long)c->sm_count * c->blocks_per_sm;
+    const long long per_cta = (long long)(rt::kPoolBlock / 32) * rt::kPoolSlots;   // slots one CTA keeps in flight
+    const long long need = (long long)((items + per_cta - 1) / per_cta);
+    if (grid > need) grid = need;
+    CUDA_TRY(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->stream));
+    CUDA_TRY(cudaEventRecord(ev.first, c->stream));
+    CUDA_TRY(rt::launch_pathtrace_pool(sel, c->P, (int)grid, c->stream));
+    CUDA_TRY(cudaEventRecord(ev.second, c->stream));
+    return RTPBR_OK;
+}
+
+static int next_event_pair(RtpbrContext* c, std::pair<cudaEvent_t, cudaEvent_t>** out)
+{
     if (c->kernel_events_used == c->kernel_events.size()) {
         cudaEvent_t a, b;
         CUDA_TRY(cudaEventCreate(&a));
         CUDA_TRY(cudaEventCreate(&b));
         c->kernel_events.emplace_back(a, b);
     }
-    auto& ev = c->kernel_events[c->kernel_events_used];
+    *out = &c->kernel_events[c->kernel_events_used++];
+    return RTPBR_OK;
+}
+
+int rtpbr_pathtrace(RtpbrContext* c, int spp)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    if (spp < 1) return fail(RTPBR_ERR_ARG, "spp must be >= 1");
+    if (!c->have_scene || !c->have_camera) return fail(RTPBR_ERR_STATE, "set_scene and set_camera must precede pathtrace");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const rt::KernelSelect sel = select_kernel(c);
     if (c->P.total_work == 0) {  // this rank owns no columns
         c->sample_base += (uint32_t)spp;
         return RTPBR_OK;
     }
+    std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+    int rc;
     if (c->cfg.kernel == RTPBR_KERNEL_SIMPLE) {
-        CUDA_TRY(cudaEventRecord(ev.first, c->stream));
+        c->P.spp = spp;
+        c->P.sample_base = c->sample_base;
+        if ((rc = next_event_pair(c, &ev)) != RTPBR_OK) return rc;
+        CUDA_TRY(cudaEventRecord(ev->first, c->stream));
         CUDA_TRY(rt::launch_pathtrace_simple(sel, c->P, c->stream));
-        CUDA_TRY(cudaEventRecord(ev.second, c->stream));
+        CUDA_TRY(cudaEventRecord(ev->second, c->stream));
+        c->launches++;
+    } else if (c->cfg.family == RTPBR_FAMILY_C) {
+        c->P.spp = spp;
+        c->P.sample_base = c->sample_base;
+        if ((rc = next_event_pair(c, &ev)) != RTPBR_OK) return rc;
+        if ((rc = launch_pool_chunk(c, sel, *ev, c->P.total_work)) != RTPBR_OK) return rc;
+        c->launches++;
     } else {
-        if (c->blocks_per_sm == 0) {
-            CUDA_TRY(rt::pool_occupancy(sel, &c->blocks_per_sm));
-            if (c->blocks_per_sm < 1) return fail(RTPBR_ERR_CUDA, "pool kernel does not fit on an SM");
+        size_t budget = (size_t)4096 << 20;
+        if (const char* e = getenv("RTPBR_SCRATCH_MB")) {
+            long long v = atoll(e);
+            if (v >= 1) budget = (size_t)v << 20;
         }
-        int grid = c->sm_count * c->blocks_per_sm;
-        // one CTA keeps (warps x pool slots) pixels in flight
-        const long long per_cta = (long long)(rt::kPoolBlock / 32) * rt::kPoolSlots;
-        const long long need = ((long long)c->P.total_work + per_cta - 1) / per_cta;
-        if ((long long)grid > need) grid = (int)need;
-        CUDA_TRY(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->stream));
-        CUDA_TRY(cudaEventRecord(ev.first, c->stream));
-        CUDA_TRY(rt::launch_pathtrace_pool(sel, c->P, grid, c->stream));
-        CUDA_TRY(cudaEventRecord(ev.second, c->stream));
+        long long chunk = (long long)(budget / ((size_t)c->P.total_work * sizeof(float4)));
+        if (chunk < 1) chunk = 1;
+        if (chunk > spp) chunk = spp;
+        const size_t need_bytes = (size_t)c->P.total_work * (size_t)chunk * sizeof(float4);
+        if (need_bytes > c->scratch_bytes) {
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            if (c->d_scratch) { cudaFree(c->d_scratch); c->d_scratch = nullptr; c->scratch_bytes = 0; }
+            CUDA_TRY(cudaMalloc(&c->d_scratch, need_bytes));
+            c->scratch_bytes = need_bytes;
+        }
+        c->P.scratch = c->d_scratch;
+        for (int done = 0; done < spp; done += (int)chunk) {
+            const int n = spp - done < (int)chunk ? spp - done : (int)chunk;
+            c->P.spp = n;
+            c->P.sample_base = c->sample_base + (uint32_t)done;
+            if ((rc = next_event_pair(c, &ev)) != RTPBR_OK) return rc;
+            if ((rc = launch_pool_chunk(c, sel, *ev, (unsigned long long)c->P.total_work * (unsigned long long)n)) != RTPBR_OK)
+                return rc;
+            CUDA_TRY(rt::launch_fold_samples(c->P, c->stream));
+            c->launches += 2;
+        }
     }
-    c->kernel_events_used++;
-    c->launches++;
     c->sample_base += (uint32_t)spp;
     return RTPBR_OK;
 }

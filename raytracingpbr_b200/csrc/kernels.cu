@@ -19,9 +19,12 @@ constexpr unsigned kFull = 0xffffffffu;
 // Wavefront pool kernel.
 //
 // Every warp owns a pool of NSLOT path slots in shared memory (structure of arrays, one word
-// per field per slot).  A slot is a pixel worker: it traces the samples of one pixel one after
-// the other (so the fp32 accumulation order equals the reference's launch-by-launch
-// `buffer += color`), then pulls the next pixel from the global work queue.
+// per field per slot).  Families A/B: a slot traces ONE sample (work item = (pixel, sample)),
+// writes its radiance to the per-sample scratch buffer in HBM and pulls the next item from the
+// global work queue; k_fold_samples then adds a pixel's samples in sample order, so the fp32
+// accumulation order equals the reference's launch-by-launch `buffer += color` while the work
+// granularity is a single path (no ragged tail: 67 M items on C1).  Family C: a slot is a pixel
+// worker, because its launches are sequentially dependent through ray_buffer.
 //
 // The warp alternates between two phases, both at (nearly) full lane occupancy:
 //   MARCH    each lane holds the march state of one slot in registers and the warp-wide loop
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(kPoolBlock, kPoolMinBlocks) k_pathtrace_pool(c
                 Path p;
                 int st = ST_NONE, samp = 0, k = 0;
                 uint32_t pixel = 0;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned long long wid = 0;                       // families A/B: work item = scratch index
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);     // family C: the pixel's image_buffer entry
                 p.m = m;
                 p.col = V3(0.f);
                 p.depth = 0;
@@ -160,8 +164,12 @@ __global__ void __launch_bounds__(kPoolBlock, kPoolMinBlocks) k_pathtrace_pool(c
                     samp = pool.geti(F_SAMP, slot);
                     k = pool.geti(F_K, slot);
                     p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, (uint32_t)pool.geti(F_RNGN, slot));
-                    acc = make_float4(pool.getf(F_ACCX, slot), pool.getf(F_ACCY, slot), pool.getf(F_ACCZ, slot),
-                                      pool.getf(F_ACCW, slot));
+                    if (VAR::FAMILY == FAMILY_C)
+                        acc = make_float4(pool.getf(F_ACCX, slot), pool.getf(F_ACCY, slot), pool.getf(F_ACCZ, slot),
+                                          pool.getf(F_ACCW, slot));
+                    else
+                        wid = (unsigned long long)(uint32_t)pool.geti(F_ACCX, slot) |
+                              ((unsigned long long)(uint32_t)pool.geti(F_ACCY, slot) << 32);
                 }
                 int pi = (int)(pixel / (uint32_t)P.height), pj = (int)(pixel - (uint32_t)pi * (uint32_t)P.height);
 
@@ -199,37 +207,42 @@ __global__ void __launch_bounds__(kPoolBlock, kPoolMinBlocks) k_pathtrace_pool(c
                             }
                         }
                     } else if (st == ST_DONE) {
-                        acc.x += p.col.x; acc.y += p.col.y; acc.z += p.col.z; acc.w += 1.0f;
-                        if (++samp == P.spp) {
-                            P.image_buffer[pixel] = acc;
-                            st = ST_FETCH;
-                        } else {
-                            st = ST_NEWPATH;
-                        }
+                        P.scratch[wid] = make_float4(p.col.x, p.col.y, p.col.z, 1.0f);   // vec4(ray.color, 1.0)
+                        st = ST_FETCH;
                     }
                     // warp-aggregated pull from the global work queue (tile padding is skipped)
                     for (;;) {
                         const unsigned m_fetch = __ballot_sync(kFull, st == ST_FETCH);
                         if (m_fetch == 0u) break;
                         const int leader = __ffs(m_fetch) - 1;
-                        unsigned base = 0;
-                        if (lane == leader) base = atomicAdd(P.work_counter, (unsigned)__popc(m_fetch));
+                        unsigned long long base = 0;
+                        if (lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m_fetch));
                         base = __shfl_sync(kFull, base, leader);
                         if (st == ST_FETCH) {
-                            const unsigned wk = base + (unsigned)__popc(m_fetch & lane_lt);
-                            if (wk >= P.total_work) {
-                                st = ST_DEAD;
-                            } else if (work_to_pixel(P, wk, pi, pj)) {
-                                pixel = (uint32_t)(pi * P.height + pj);
-                                acc = P.image_buffer[pixel];
-                                samp = 0;
-                                k = 0;
-                                if (VAR::FAMILY == FAMILY_C) {
+                            const unsigned long long wk = base + (unsigned long long)__popc(m_fetch & lane_lt);
+                            if (VAR::FAMILY == FAMILY_C) {          // work item = pixel
+                                if (wk >= (unsigned long long)P.total_work) {
+                                    st = ST_DEAD;
+                                } else if (work_to_pixel(P, (uint32_t)wk, pi, pj)) {
+                                    pixel = (uint32_t)(pi * P.height + pj);
+                                    acc = P.image_buffer[pixel];
+                                    samp = 0;
+                                    k = 0;
                                     load_ray(P.ray_buffer + (size_t)pixel * 10, p);
                                     p.rng = rng_make(pixel, P.sample_base, 0u);
                                     st = ST_ADVANCE;
+                                }
+                            } else {                                // work item = (pixel item, sample)
+                                if (wk >= (unsigned long long)P.total_work * (unsigned long long)P.spp) {
+                                    st = ST_DEAD;
                                 } else {
-                                    st = ST_NEWPATH;
+                                    const uint32_t item = (uint32_t)(wk / (unsigned long long)P.spp);
+                                    if (work_to_pixel(P, item, pi, pj)) {
+                                        pixel = (uint32_t)(pi * P.height + pj);
+                                        samp = (int)(wk - (unsigned long long)item * (unsigned long long)P.spp);
+                                        wid = wk;
+                                        st = ST_NEWPATH;
+                                    }
                                 }
                             }
                         }
@@ -254,8 +267,13 @@ __global__ void __launch_bounds__(kPoolBlock, kPoolMinBlocks) k_pathtrace_pool(c
                         pool.seti(F_SAMP, slot, samp);
                         pool.seti(F_K, slot, k);
                         pool.seti(F_RNGN, slot, (int)p.rng.n);
-                        pool.setf(F_ACCX, slot, acc.x); pool.setf(F_ACCY, slot, acc.y);
-                        pool.setf(F_ACCZ, slot, acc.z); pool.setf(F_ACCW, slot, acc.w);
+                        if (VAR::FAMILY == FAMILY_C) {
+                            pool.setf(F_ACCX, slot, acc.x); pool.setf(F_ACCY, slot, acc.y);
+                            pool.setf(F_ACCZ, slot, acc.z); pool.setf(F_ACCW, slot, acc.w);
+                        } else {
+                            pool.seti(F_ACCX, slot, (int)(uint32_t)wid);
+                            pool.seti(F_ACCY, slot, (int)(uint32_t)(wid >> 32));
+                        }
                     }
                 }
                 const unsigned rdy = __ballot_sync(kFull, slot >= 0 && st == ST_READY);
@@ -332,6 +350,26 @@ __global__ void __launch_bounds__(kSimpleBlock) k_pathtrace_simple(const __grid_
         atomicAdd(&P.counters[2], cnt.normals);
         atomicAdd(&P.counters[3], cnt.samples);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_fold_samples: image_buffer[pixel] += scratch[item * spp + s] for s = 0 .. spp-1, IN ORDER
+// (shortest:121 `buffer += vec4(ray.color, 1.0)` once per launch).  HBM-bound: 16 B per sample
+// read + 32 B per pixel; one thread per pixel item, each thread streams its own contiguous run.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fold_samples(const __grid_constant__ KParams P)
+{
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    int i, j;
+    if (item >= P.total_work || !work_to_pixel(P, item, i, j)) return;
+    const uint32_t pixel = (uint32_t)(i * P.height + j);
+    float4 acc = P.image_buffer[pixel];
+    const float4* src = P.scratch + (size_t)item * (size_t)P.spp;
+    for (int s = 0; s < P.spp; ++s) {
+        const float4 c = __ldcs(src + s);
+        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+    }
+    P.image_buffer[pixel] = acc;
 }
 
 // refresh() of src/renderer.py:12-22: the accumulators are cleared by a memset; the ray buffer keeps
@@ -482,6 +520,11 @@ bool kernel_supported(const KernelSelect& sel)
     if (sel.family == FAMILY_B) return (sel.marcher == MARCH_PLAIN && !sel.bunny) || sel.marcher == MARCH_ENHANCED;
     if (sel.family == FAMILY_C) return sel.marcher == MARCH_SRC && !sel.bunny;
     return false;
+}
+cudaError_t launch_fold_samples(const KParams& P, cudaStream_t stream)
+{
+    k_fold_samples<<<(P.total_work + 255) / 256, 256, 0, stream>>>(P);
+    return cudaGetLastError();
 }
 cudaError_t launch_refresh_depth(float* ray_buffer, int n, cudaStream_t stream)
 {

@@ -72,7 +72,8 @@ struct KParams {
     const float* rr_prob;           // [max_bounces] Russian-roulette table (families A/B)
     const float* env;               // (env_w, env_h, 3) or nullptr
     int32_t env_w, env_h;
-    unsigned int* work_counter;     // persistent-kernel work queue head
+    float4* scratch;                // families A/B: per-sample radiance, [total_work][spp] (pool kernel -> k_fold_samples)
+    unsigned long long* work_counter;   // persistent-kernel work queue head
     unsigned long long* counters;   // RTPBR_CNT_* (count_work builds)
 };
 

@@ -59,6 +59,15 @@ def test_progressive_accumulation_equals_one_launch():
     assert np.array_equal(a, oracle(96, 80, 7, 8, seed=2))
 
 
+def test_scratch_chunking_is_invisible(monkeypatch):
+    # a 1 MiB scratch budget forces one spp per chunk at 256 x 256 (pool kernel + fold per chunk)
+    want = oracle(256, 256, 5, 8, seed=3)
+    monkeypatch.setenv("RTPBR_SCRATCH_MB", "1")
+    assert np.array_equal(render(256, 256, 5, 8, seed=3), want)
+    monkeypatch.setenv("RTPBR_SCRATCH_MB", "3")
+    assert np.array_equal(render(256, 256, 5, 8, seed=3), want)
+
+
 def test_work_counters_match_oracle():
     got, cnt = render(128, 96, 3, 8, seed=4, count=True)
     want, ocnt = oracle(128, 96, 3, 8, seed=4, counters=True)
