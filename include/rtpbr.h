@@ -182,6 +182,18 @@ RTPBR_API int rtpbr_kernel_time(RtpbrContext* ctx, float* kernel_ms, int* launch
 RTPBR_API int rtpbr_get_counters(RtpbrContext* ctx, uint64_t out[RTPBR_CNT_COUNT]);
 RTPBR_API int rtpbr_device_info(RtpbrContext* ctx, int* sm_count, int* cc_major, int* cc_minor, int* blocks_per_sm);
 
+/* Scene-specialised kernels.  Like Taichi, which JIT-compiles the reference's kernels per scene
+ * (`ti.static` object loops, src/scene.py:48-51), rtpbr_pathtrace compiles the march loop for the
+ * current scene with NVRTC (object constants as immediates; bit-identical results).  Enabled by
+ * default (RTPBR_JIT=0 or rtpbr_set_jit(ctx, 0) selects the ahead-of-time kernels; so does any
+ * NVRTC failure).  rtpbr_jit_status returns 1 when the specialised kernel is in use and copies a
+ * one-line description to buf.  rtpbr_jit_generate / rtpbr_jit_compile_check need no GPU:
+ * they return the generated source (its length) / run NVRTC on it (0 on success). */
+RTPBR_API int rtpbr_set_jit(RtpbrContext* ctx, int enable);
+RTPBR_API int rtpbr_jit_status(RtpbrContext* ctx, char* buf, size_t cap);
+RTPBR_API long long rtpbr_jit_generate(const RtpbrConfig* cfg, const RtpbrObject* objects, int n, char* buf, size_t cap);
+RTPBR_API int rtpbr_jit_compile_check(const RtpbrConfig* cfg, const RtpbrObject* objects, int n, char* log, size_t cap);
+
 /* multi-GPU: one context per process/GPU; NCCL only at tonemap time */
 RTPBR_API int rtpbr_nccl_unique_id(void* id128);                       /* 128 bytes out (rank 0) */
 RTPBR_API int rtpbr_nccl_init(RtpbrContext* ctx, const void* id128, int rank, int nranks);

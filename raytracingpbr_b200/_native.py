@@ -32,7 +32,7 @@ EXPORTS = (
     "rtpbr_set_sample_base", "rtpbr_set_shard", "rtpbr_refresh", "rtpbr_pathtrace", "rtpbr_post_process",
     "rtpbr_download", "rtpbr_upload", "rtpbr_sync", "rtpbr_flush_l2", "rtpbr_timer_start", "rtpbr_timer_stop", "rtpbr_kernel_time",
     "rtpbr_get_counters", "rtpbr_device_info", "rtpbr_nccl_unique_id", "rtpbr_nccl_init", "rtpbr_reduce_tiles",
-    "rtpbr_device_ptr", "rtpbr_last_error", "rtpbr_version", "rtpbr_sizeof_config", "rtpbr_sizeof_object",
+    "rtpbr_device_ptr", "rtpbr_set_jit", "rtpbr_jit_status", "rtpbr_jit_generate", "rtpbr_jit_compile_check", "rtpbr_last_error", "rtpbr_version", "rtpbr_sizeof_config", "rtpbr_sizeof_object",
     "rtpbr_sizeof_camera",
 )
 
@@ -127,12 +127,17 @@ def lib() -> C.CDLL:
         "rtpbr_nccl_init": [vp, vp, C.c_int, C.c_int],
         "rtpbr_reduce_tiles": [vp, C.c_int],
         "rtpbr_device_ptr": [vp, C.c_int, C.POINTER(C.c_uint64)],
+        "rtpbr_set_jit": [vp, C.c_int],
+        "rtpbr_jit_status": [vp, C.c_char_p, C.c_size_t],
+        "rtpbr_jit_compile_check": [C.POINTER(RtpbrConfig), C.POINTER(RtpbrObject), C.c_int, C.c_char_p, C.c_size_t],
         "rtpbr_version": [], "rtpbr_sizeof_config": [], "rtpbr_sizeof_object": [], "rtpbr_sizeof_camera": [],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    L.rtpbr_jit_generate.argtypes = [C.POINTER(RtpbrConfig), C.POINTER(RtpbrObject), C.c_int, C.c_char_p, C.c_size_t]
+    L.rtpbr_jit_generate.restype = C.c_longlong
     L.rtpbr_last_error.argtypes = []
     L.rtpbr_last_error.restype = C.c_char_p
     if L.rtpbr_sizeof_config() != C.sizeof(RtpbrConfig) or L.rtpbr_sizeof_object() != C.sizeof(RtpbrObject) \
@@ -145,6 +150,41 @@ def lib() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise RtpbrError(rc, (lib().rtpbr_last_error() or b"").decode("utf-8", "replace"))
+
+
+def jit_source(cfg: RtpbrConfig, objects) -> str:
+    """The scene-specialised translation unit rtpbr_pathtrace would compile (no GPU needed)."""
+    arr = (RtpbrObject * len(objects))(*objects)
+    n = lib().rtpbr_jit_generate(C.byref(cfg), arr, len(objects), None, 0)
+    if n < 0:
+        check(int(n))
+    buf = C.create_string_buffer(int(n) + 1)
+    lib().rtpbr_jit_generate(C.byref(cfg), arr, len(objects), buf, int(n) + 1)
+    return buf.value.decode()
+
+
+def jit_compile_check(cfg: RtpbrConfig, objects) -> str:
+    """Run NVRTC on the specialised source (no GPU needed); returns the compiler log, raises on failure."""
+    _point_at_nvrtc()
+    arr = (RtpbrObject * len(objects))(*objects)
+    log = C.create_string_buffer(1 << 16)
+    check(lib().rtpbr_jit_compile_check(C.byref(cfg), arr, len(objects), log, len(log)))
+    return log.value.decode()
+
+
+def _point_at_nvrtc() -> None:
+    """Help librtpbr find the pip-installed NVRTC when the CUDA toolkit's is not on the loader path."""
+    if os.environ.get("RTPBR_NVRTC_LIB"):
+        return
+    import importlib.util
+    spec = importlib.util.find_spec("nvidia")
+    if spec is None or not spec.submodule_search_locations:
+        return
+    for base in spec.submodule_search_locations:
+        p = os.path.join(base, "cuda_nvrtc", "lib", "libnvrtc.so.12")
+        if os.path.exists(p) and not os.path.exists("/usr/local/cuda/lib64/libnvrtc.so.12"):
+            os.environ["RTPBR_NVRTC_LIB"] = p
+            return
 
 
 def _find_nccl() -> str | None:
@@ -168,6 +208,7 @@ class Context:
         self.cfg = cfg
         self.width, self.height = cfg.width, cfg.height
         h = C.c_void_p()
+        _point_at_nvrtc()
         check(self._L.rtpbr_create(C.byref(cfg), device, C.byref(h)))
         self._h = h
         self._keep = []
@@ -223,6 +264,17 @@ class Context:
 
     def sync(self) -> None:
         check(self._L.rtpbr_sync(self._h))
+
+    def set_jit(self, enable: bool) -> None:
+        check(self._L.rtpbr_set_jit(self._h, int(enable)))
+
+    def jit_status(self):
+        """(active, description) of the scene-specialised kernel."""
+        buf = C.create_string_buffer(4096)
+        rc = self._L.rtpbr_jit_status(self._h, buf, len(buf))
+        if rc < 0:
+            check(rc)
+        return bool(rc), buf.value.decode("utf-8", "replace")
 
     def flush_l2(self) -> None:
         check(self._L.rtpbr_flush_l2(self._h))

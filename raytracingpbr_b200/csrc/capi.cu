@@ -5,12 +5,15 @@
 
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/rtpbr.h"
 #include "host_setup.h"
+#include "jit.h"
+#include "jit_codegen.h"
 #include "kernels.h"
 
 namespace {
@@ -90,8 +93,15 @@ struct RtpbrContext {
     unsigned long long* d_counters = nullptr;
     void* d_flush = nullptr;
     bool have_scene = false, have_camera = false, has_bunny = false;
+    std::vector<RtpbrObject> scene;
     uint32_t sample_base = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0, blocks_per_sm = 0;
+    bool blocks_per_sm_is_jit = false;
+    // scene-specialised kernel (NVRTC); falls back to the ahead-of-time variant when unavailable
+    bool jit_enabled = true, jit_stale = true;
+    std::unique_ptr<rt::jit::Kernel> jit_kernel;
+    int jit_blocks_per_sm = 0;
+    std::string jit_log = "not built yet";
     void* nccl_comm = nullptr;
     int nccl_rank = 0, nccl_nranks = 1;
     unsigned long long launches = 0;
@@ -170,6 +180,7 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     rt::fill_config(c->P, c->cfg);
     rt::fill_shard(c->P, 0, 1, 32);
     rt::fill_frame(c->P, 0);
+    if (const char* j = getenv("RTPBR_JIT")) c->jit_enabled = atoi(j) != 0;
     c->P.resolve_min = 8;
     if (const char* q = getenv("RTPBR_RESOLVE_MIN")) {
         int v = atoi(q);
@@ -256,6 +267,8 @@ int rtpbr_set_scene(RtpbrContext* c, const RtpbrObject* objects, int n)
                                            "(the neural bunny needs family B with the enhanced marcher)");
     rt::fill_objects(c->P, objects, n);
     c->has_bunny = bunny;
+    c->scene.assign(objects, objects + n);
+    c->jit_stale = true;
     c->have_scene = true;
     c->blocks_per_sm = 0;  // kernel variant may change with the object count
     return RTPBR_OK;
@@ -322,11 +335,59 @@ int rtpbr_refresh(RtpbrContext* c)
 //   buffer ([pixel items][chunk] float4) stays within the scratch budget (RTPBR_SCRATCH_MB, default
 //   4096); per chunk: k_pathtrace_pool (work item = one path) then k_fold_samples (ordered sum).
 //   family C / simple kernel: one launch.
+// Build (or reuse) the scene-specialised kernel.  Any failure disables JIT for this context and
+// leaves the ahead-of-time kernel in charge; the reason is kept for rtpbr_jit_status().
+static void ensure_jit(RtpbrContext* c)
+{
+    if (!c->jit_enabled || !c->jit_stale) return;
+    c->jit_stale = false;
+    c->jit_kernel.reset();
+    if (c->cfg.count_work) { c->jit_log = "disabled: count_work uses the ahead-of-time counting kernel"; return; }
+    const rt::jit::Source src = rt::jit::generate(c->cfg, c->scene.data(), (int)c->scene.size());
+    std::shared_ptr<std::vector<char>> cubin;
+    std::string log;
+    if (!rt::jit::compile(src.text, rt::jit::default_include_dir(), cubin, log)) {
+        c->jit_enabled = false;
+        c->jit_log = "NVRTC failed, using the ahead-of-time kernel: " + log;
+        fprintf(stderr, "librtpbr: %s\n", c->jit_log.c_str());
+        return;
+    }
+    std::unique_ptr<rt::jit::Kernel> k(new rt::jit::Kernel());
+    std::string err;
+    if (!rt::jit::load(*cubin, src.kernel_name.c_str(), rt::pool_dynamic_smem(), *k, err) ||
+        !rt::jit::occupancy(*k, rt::kPoolBlock, rt::pool_dynamic_smem(), &c->jit_blocks_per_sm, err) || c->jit_blocks_per_sm < 1) {
+        c->jit_enabled = false;
+        c->jit_log = "loading the specialised kernel failed, using the ahead-of-time kernel: " + err;
+        fprintf(stderr, "librtpbr: %s\n", c->jit_log.c_str());
+        return;
+    }
+    c->jit_log = "scene-specialised kernel active (" + std::to_string(k->registers) + " registers, " +
+                 std::to_string(c->jit_blocks_per_sm) + " CTAs/SM)";
+    c->jit_kernel = std::move(k);
+}
+
 static int launch_pool_chunk(RtpbrContext* c, const rt::KernelSelect& sel, std::pair<cudaEvent_t, cudaEvent_t>& ev,
                              unsigned long long items)
 {
-    if (c->blocks_per_sm == 0) {
+    ensure_jit(c);
+    if (c->jit_kernel) {
+        long long grid = (long long)c->sm_count * c->jit_blocks_per_sm;
+        const long long per_cta = (long long)(rt::kPoolBlock / 32) * rt::kPoolSlots;
+        const long long need = (long long)((items + per_cta - 1) / per_cta);
+        if (grid > need) grid = need;
+        CUDA_TRY(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->stream));
+        CUDA_TRY(cudaEventRecord(ev.first, c->stream));
+        std::string err;
+        if (!rt::jit::launch(*c->jit_kernel, c->P, (int)grid, rt::kPoolBlock, rt::pool_dynamic_smem(), c->stream, err))
+            return fail(RTPBR_ERR_CUDA, err);
+        CUDA_TRY(cudaEventRecord(ev.second, c->stream));
+        c->blocks_per_sm = c->jit_blocks_per_sm;
+        c->blocks_per_sm_is_jit = true;
+        return RTPBR_OK;
+    }
+    if (c->blocks_per_sm == 0 || c->blocks_per_sm_is_jit) {
         CUDA_TRY(rt::pool_occupancy(sel, &c->blocks_per_sm));
+        c->blocks_per_sm_is_jit = false;
         if (c->blocks_per_sm < 1) return fail(RTPBR_ERR_CUDA, "pool kernel does not fit on an SM");
     }
     long long grid = (long long)c->sm_count * c->blocks_per_sm;
@@ -541,6 +602,61 @@ int rtpbr_device_ptr(RtpbrContext* c, int which, uint64_t* ptr)
     int rc = buffer_of(c, which, &d, &n);
     if (rc != RTPBR_OK) return rc;
     *ptr = (uint64_t)(uintptr_t)d;
+    return RTPBR_OK;
+}
+
+// ------------------------------------------------------------------------------ JIT
+int rtpbr_set_jit(RtpbrContext* c, int enable)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    c->jit_enabled = enable != 0;
+    c->jit_stale = true;
+    if (!c->jit_enabled) { c->jit_kernel.reset(); c->jit_log = "disabled by rtpbr_set_jit"; c->blocks_per_sm = 0; }
+    return RTPBR_OK;
+}
+
+int rtpbr_jit_status(RtpbrContext* c, char* buf, size_t cap)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    if (buf && cap > 0) {
+        strncpy(buf, c->jit_log.c_str(), cap - 1);
+        buf[cap - 1] = '\0';
+    }
+    return c->jit_kernel ? 1 : 0;
+}
+
+static int jit_validate(const RtpbrConfig* cfg, const RtpbrObject* objects, int n)
+{
+    if (!cfg || !objects) return fail(RTPBR_ERR_ARG, "null argument");
+    if (n < 1 || n > RTPBR_MAX_OBJECTS) return fail(RTPBR_ERR_ARG, "object count must be in 1..RTPBR_MAX_OBJECTS");
+    return validate_config(*cfg);
+}
+
+long long rtpbr_jit_generate(const RtpbrConfig* cfg, const RtpbrObject* objects, int n, char* buf, size_t cap)
+{
+    int rc = jit_validate(cfg, objects, n);
+    if (rc != RTPBR_OK) return rc;
+    const rt::jit::Source src = rt::jit::generate(*cfg, objects, n);
+    if (buf && cap > 0) {
+        strncpy(buf, src.text.c_str(), cap - 1);
+        buf[cap - 1] = '\0';
+    }
+    return (long long)src.text.size();
+}
+
+int rtpbr_jit_compile_check(const RtpbrConfig* cfg, const RtpbrObject* objects, int n, char* log, size_t cap)
+{
+    int rc = jit_validate(cfg, objects, n);
+    if (rc != RTPBR_OK) return rc;
+    const rt::jit::Source src = rt::jit::generate(*cfg, objects, n);
+    std::shared_ptr<std::vector<char>> cubin;
+    std::string l;
+    const bool ok = rt::jit::compile(src.text, rt::jit::default_include_dir(), cubin, l);
+    if (log && cap > 0) {
+        strncpy(log, l.c_str(), cap - 1);
+        log[cap - 1] = '\0';
+    }
+    if (!ok) return fail(RTPBR_ERR_UNSUPPORTED, l);
     return RTPBR_OK;
 }
 

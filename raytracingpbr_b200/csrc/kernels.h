@@ -2,14 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "kernels_config.h"
 #include "rt_params.h"
 
 namespace rt {
 
-constexpr int kPoolBlock = 256;        // 8 warps per CTA
-constexpr int kPoolMinBlocks = 4;      // <= 64 registers/thread -> 32 warps per SM
-constexpr int kPoolSlots = 64;         // path slots per warp: 32 marching + 32 ready / pending
-constexpr int kSimpleBlock = 128;
 
 struct KernelSelect {
     int family;
@@ -20,6 +17,7 @@ struct KernelSelect {
 };
 
 bool kernel_supported(const KernelSelect& sel);
+size_t pool_dynamic_smem();
 cudaError_t launch_pathtrace_pool(const KernelSelect& sel, const KParams& P, int grid, cudaStream_t stream);
 cudaError_t launch_pathtrace_simple(const KernelSelect& sel, const KParams& P, cudaStream_t stream);
 cudaError_t pool_occupancy(const KernelSelect& sel, int* blocks_per_sm);

@@ -1,0 +1,326 @@
+// pool_kernel.cuh -- the wavefront pool kernel template.  Included by kernels.cu (ahead-of-time
+// variants) and by the scene-specialised translation units that jit.cu compiles with NVRTC.
+#pragma once
+#include "kernels_config.h"
+#include "rt_integrator.cuh"
+
+namespace rt {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------
+// Wavefront pool kernel.
+//
+// Every warp owns a pool of NSLOT path slots in shared memory (structure of arrays, one word
+// per field per slot).  Families A/B: a slot traces ONE sample (work item = (pixel, sample)),
+// writes its radiance to the per-sample scratch buffer in HBM and pulls the next item from the
+// global work queue; k_fold_samples then adds a pixel's samples in sample order, so the fp32
+// accumulation order equals the reference's launch-by-launch `buffer += color` while the work
+// granularity is a single path (no ragged tail: 67 M items on C1).  Family C: a slot is a pixel
+// worker, because its launches are sequentially dependent through ray_buffer.
+//
+// The warp alternates between two phases, both at (nearly) full lane occupancy:
+//   MARCH    each lane holds the march state of one slot in registers and the warp-wide loop
+//            body is ONE sphere-tracing step (scene SDF evaluation).  A lane whose ray hits /
+//            leaves / runs out of steps writes the result to its slot, pushes the slot on the
+//            warp's `pending` stack and pops a ready-to-march slot from the `ready` stack.
+//   RESOLVE  when lanes would idle (ready stack empty) the marching lanes park their slots and
+//            all 32 lanes pop pending slots: surface interaction (normal, BSDF sample,
+//            Russian roulette), sample accumulation, path regeneration, and warp-aggregated
+//            work-queue pulls.  Resolved slots go back on the ready stack.
+// With NSLOT = 64 the pool holds 32 marching + 32 ready/pending slots, so the heavy-tailed
+// march lengths (p50 28, p99 ~100 steps) no longer idle lanes, and the divergent shading code
+// runs on compacted batches.  The RNG is keyed by (pixel, sample, draw index) only, so the
+// scheduling cannot change any number a sample sees: results are bit-identical to the simple
+// kernel and to the CPU oracle.
+// ------------------------------------------------------------------------------------------
+enum : int { ST_NONE = 0, ST_READY = 1, ST_HIT = 2, ST_MISS = 3, ST_DONE = 4, ST_FETCH = 5, ST_NEWPATH = 6,
+             ST_ADVANCE = 7, ST_DEAD = 8 };
+
+// slot fields (word index into the per-warp SoA)
+enum : int { F_ROX = 0, F_ROY, F_ROZ, F_RDX, F_RDY, F_RDZ, F_COLX, F_COLY, F_COLZ, F_T, F_W, F_S, F_D, F_TEVAL,
+             F_STEPS, F_IDX, F_DEPTH, F_RNGN, F_PIXEL, F_SAMP, F_K, F_STATUS, F_ACCX, F_ACCY, F_ACCZ, F_ACCW,
+             F_COUNT };
+
+template <int NSLOT>
+struct Pool {
+    uint32_t* w;   // [F_COUNT][NSLOT]
+    __device__ __forceinline__ float getf(int f, int slot) const { return __uint_as_float(w[f * NSLOT + slot]); }
+    __device__ __forceinline__ int geti(int f, int slot) const { return (int)w[f * NSLOT + slot]; }
+    __device__ __forceinline__ void setf(int f, int slot, float v) { w[f * NSLOT + slot] = __float_as_uint(v); }
+    __device__ __forceinline__ void seti(int f, int slot, int v) { w[f * NSLOT + slot] = (uint32_t)v; }
+};
+
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void load_march(const Pool<NSLOT>& pool, int slot, MarchState& m)
+{
+    m.ro = V3(pool.getf(F_ROX, slot), pool.getf(F_ROY, slot), pool.getf(F_ROZ, slot));
+    m.rd = V3(pool.getf(F_RDX, slot), pool.getf(F_RDY, slot), pool.getf(F_RDZ, slot));
+    m.t = pool.getf(F_T, slot);
+    m.steps = pool.geti(F_STEPS, slot);
+    m.idx = pool.geti(F_IDX, slot);
+    m.t_eval = pool.getf(F_TEVAL, slot);
+    if (VAR::MARCHER != MARCH_PLAIN) {
+        m.w = pool.getf(F_W, slot); m.s = pool.getf(F_S, slot); m.d = pool.getf(F_D, slot);
+    } else {
+        m.w = 1.0f; m.s = 0.0f; m.d = 0.0f;
+    }
+}
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void store_march(Pool<NSLOT>& pool, int slot, const MarchState& m, bool with_ray)
+{
+    if (with_ray || VAR::MARCHER == MARCH_SRC) {
+        pool.setf(F_ROX, slot, m.ro.x); pool.setf(F_ROY, slot, m.ro.y); pool.setf(F_ROZ, slot, m.ro.z);
+    }
+    if (with_ray) {
+        pool.setf(F_RDX, slot, m.rd.x); pool.setf(F_RDY, slot, m.rd.y); pool.setf(F_RDZ, slot, m.rd.z);
+    }
+    pool.setf(F_T, slot, m.t);
+    pool.seti(F_STEPS, slot, m.steps);
+    pool.seti(F_IDX, slot, m.idx);
+    pool.setf(F_TEVAL, slot, m.t_eval);
+    if (VAR::MARCHER != MARCH_PLAIN) {
+        pool.setf(F_W, slot, m.w); pool.setf(F_S, slot, m.s); pool.setf(F_D, slot, m.d);
+    }
+}
+
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void pool_body(const KParams& P)
+{
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lane_lt = (1u << lane) - 1u;
+    constexpr int kWarpWords = F_COUNT * NSLOT + 2 * (NSLOT / 4);
+    Pool<NSLOT> pool;
+    pool.w = smem + warp * kWarpWords;
+    uint8_t* ready = reinterpret_cast<uint8_t*>(pool.w + F_COUNT * NSLOT);
+    uint8_t* pend = ready + NSLOT;
+    int n_ready = 0, n_pend = NSLOT;          // warp-uniform
+
+    for (int s = lane; s < NSLOT; s += 32) {
+        pool.seti(F_STATUS, s, ST_FETCH);
+        pend[s] = (uint8_t)s;
+    }
+    __syncwarp();
+
+    int my = -1;
+    MarchState m;
+    m.ro = m.rd = V3(0.f); m.t = m.w = m.s = m.d = m.t_eval = 0.f; m.steps = m.idx = 0;
+    WorkCounters cnt = { 0, 0, 0, 0 };
+    unsigned long long c_iters = 0, c_active = 0, c_rounds = 0, c_resolved = 0;
+
+    for (;;) {
+        // ---------------------------------------------------------------- acquire ready slots
+        const unsigned needy = __ballot_sync(kFull, my < 0);
+        if (needy != 0u && n_ready > 0) {
+            const int r = __popc(needy & lane_lt);
+            if (my < 0 && r < n_ready) {
+                my = ready[n_ready - 1 - r];
+                load_march<VAR, NSLOT>(pool, my, m);
+            }
+            n_ready -= min(__popc(needy), n_ready);
+        }
+        const unsigned active = __ballot_sync(kFull, my >= 0);
+
+        // ---------------------------------------------------------------- resolve phase
+        if (active != kFull && n_pend > 0 && (n_pend >= P.resolve_min || active == 0u)) {
+            if (VAR::COUNT) c_rounds++;
+            if (my >= 0) {   // park: the slot stays ready-to-march
+                store_march<VAR, NSLOT>(pool, my, m, false);
+                ready[n_ready + __popc(active & lane_lt)] = (uint8_t)my;
+                my = -1;
+            }
+            n_ready += __popc(active);
+            __syncwarp();
+            while (n_pend > 0) {
+                const int take = min(n_pend, 32);
+                const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
+                n_pend -= take;
+                if (VAR::COUNT) c_resolved += (unsigned long long)take;
+
+                // ---- load the slot
+                Path p;
+                int st = ST_NONE, samp = 0, k = 0;
+                uint32_t pixel = 0;
+                unsigned long long wid = 0;                       // families A/B: work item = scratch index
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);     // family C: the pixel's image_buffer entry
+                p.m = m;
+                p.col = V3(0.f);
+                p.depth = 0;
+                p.rng = rng_make(0u, 0u, 0u);
+                if (slot >= 0) {
+                    st = pool.geti(F_STATUS, slot);
+                    load_march<VAR, NSLOT>(pool, slot, p.m);
+                    p.col = V3(pool.getf(F_COLX, slot), pool.getf(F_COLY, slot), pool.getf(F_COLZ, slot));
+                    p.depth = pool.geti(F_DEPTH, slot);
+                    pixel = (uint32_t)pool.geti(F_PIXEL, slot);
+                    samp = pool.geti(F_SAMP, slot);
+                    k = pool.geti(F_K, slot);
+                    p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, (uint32_t)pool.geti(F_RNGN, slot));
+                    if (VAR::FAMILY == FAMILY_C)
+                        acc = make_float4(pool.getf(F_ACCX, slot), pool.getf(F_ACCY, slot), pool.getf(F_ACCZ, slot),
+                                          pool.getf(F_ACCW, slot));
+                    else
+                        wid = (unsigned long long)(uint32_t)pool.geti(F_ACCX, slot) |
+                              ((unsigned long long)(uint32_t)pool.geti(F_ACCY, slot) << 32);
+                }
+                int pi = (int)(pixel / (uint32_t)P.height), pj = (int)(pixel - (uint32_t)pi * (uint32_t)P.height);
+
+                // ---- run the slot's state machine until it needs marching again (or dies)
+                if (VAR::FAMILY == FAMILY_C) {
+                    if (st == ST_HIT || st == ST_MISS) {
+                        c_after_march<VAR>(P, p, st == ST_HIT ? MARCH_HIT : MARCH_MISS, VAR::COUNT ? &cnt : nullptr);
+                        k++;
+                        st = ST_ADVANCE;
+                    }
+                } else {
+                    if (st == ST_HIT) {
+                        if (VAR::COUNT) { cnt.normals++; cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                        st = (on_hit<VAR>(P, p) && begin_bounce<VAR>(P, p)) ? ST_READY : ST_DONE;
+                    } else if (st == ST_MISS) {
+                        if (VAR::COUNT) { cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                        on_miss<VAR>(P, p);
+                        st = ST_DONE;
+                    }
+                }
+                for (;;) {
+                    if (VAR::FAMILY == FAMILY_C) {
+                        if (st == ST_ADVANCE) {
+                            TaskC task; task.launch = samp; task.k = k;
+                            if (c_advance<VAR>(P, pi, pj, p, task, acc, VAR::COUNT ? &cnt : nullptr)) {
+                                st = ST_READY;
+                                k = task.k;
+                            } else if (++samp == P.spp) {      // all reference launches replayed: persist the ray
+                                store_ray(P.ray_buffer + (size_t)pixel * 10, p);
+                                P.image_buffer[pixel] = acc;
+                                st = ST_FETCH;
+                            } else {
+                                p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, 0u);
+                                k = 0;
+                            }
+                        }
+                    } else if (st == ST_DONE) {
+                        P.scratch[wid] = make_float4(p.col.x, p.col.y, p.col.z, 1.0f);   // vec4(ray.color, 1.0)
+                        st = ST_FETCH;
+                    }
+                    // warp-aggregated pull from the global work queue (tile padding is skipped)
+                    for (;;) {
+                        const unsigned m_fetch = __ballot_sync(kFull, st == ST_FETCH);
+                        if (m_fetch == 0u) break;
+                        const int leader = __ffs(m_fetch) - 1;
+                        unsigned long long base = 0;
+                        if (lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m_fetch));
+                        base = __shfl_sync(kFull, base, leader);
+                        if (st == ST_FETCH) {
+                            const unsigned long long wk = base + (unsigned long long)__popc(m_fetch & lane_lt);
+                            if (VAR::FAMILY == FAMILY_C) {          // work item = pixel
+                                if (wk >= (unsigned long long)P.total_work) {
+                                    st = ST_DEAD;
+                                } else if (work_to_pixel(P, (uint32_t)wk, pi, pj)) {
+                                    pixel = (uint32_t)(pi * P.height + pj);
+                                    acc = P.image_buffer[pixel];
+                                    samp = 0;
+                                    k = 0;
+                                    load_ray(P.ray_buffer + (size_t)pixel * 10, p);
+                                    p.rng = rng_make(pixel, P.sample_base, 0u);
+                                    st = ST_ADVANCE;
+                                }
+                            } else {                                // work item = (pixel item, sample)
+                                if (wk >= (unsigned long long)P.total_work * (unsigned long long)P.spp) {
+                                    st = ST_DEAD;
+                                } else {
+                                    const uint32_t item = (uint32_t)(wk / (unsigned long long)P.spp);
+                                    if (work_to_pixel(P, item, pi, pj)) {
+                                        pixel = (uint32_t)(pi * P.height + pj);
+                                        samp = (int)(wk - (unsigned long long)item * (unsigned long long)P.spp);
+                                        wid = wk;
+                                        st = ST_NEWPATH;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (VAR::FAMILY != FAMILY_C && st == ST_NEWPATH) {
+                        if (VAR::COUNT) cnt.samples++;
+                        begin_path<VAR>(P, pixel, pi, pj, P.sample_base + (uint32_t)samp, p);
+                        st = begin_bounce<VAR>(P, p) ? ST_READY : ST_DONE;
+                    }
+                    const bool more = VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE);
+                    if (__ballot_sync(kFull, more) == 0u) break;
+                }
+
+                // ---- write the slot back; ready slots go on the ready stack
+                if (slot >= 0) {
+                    pool.seti(F_STATUS, slot, st);
+                    if (st == ST_READY) {
+                        store_march<VAR, NSLOT>(pool, slot, p.m, true);
+                        pool.setf(F_COLX, slot, p.col.x); pool.setf(F_COLY, slot, p.col.y); pool.setf(F_COLZ, slot, p.col.z);
+                        pool.seti(F_DEPTH, slot, p.depth);
+                        pool.seti(F_PIXEL, slot, (int)pixel);
+                        pool.seti(F_SAMP, slot, samp);
+                        pool.seti(F_K, slot, k);
+                        pool.seti(F_RNGN, slot, (int)p.rng.n);
+                        if (VAR::FAMILY == FAMILY_C) {
+                            pool.setf(F_ACCX, slot, acc.x); pool.setf(F_ACCY, slot, acc.y);
+                            pool.setf(F_ACCZ, slot, acc.z); pool.setf(F_ACCW, slot, acc.w);
+                        } else {
+                            pool.seti(F_ACCX, slot, (int)(uint32_t)wid);
+                            pool.seti(F_ACCY, slot, (int)(uint32_t)(wid >> 32));
+                        }
+                    }
+                }
+                const unsigned rdy = __ballot_sync(kFull, slot >= 0 && st == ST_READY);
+                if (slot >= 0 && st == ST_READY) ready[n_ready + __popc(rdy & lane_lt)] = (uint8_t)slot;
+                n_ready += __popc(rdy);
+                __syncwarp();
+            }
+            continue;
+        }
+        if (active == 0u) break;   // nothing marching, nothing pending, nothing ready: pool drained
+
+        // ---------------------------------------------------------------- march step
+        if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(active); }
+        int status = MARCH_CONTINUE;
+        if (my >= 0) status = march_step<VAR>(P, m);
+        const unsigned fin = __ballot_sync(kFull, status != MARCH_CONTINUE);
+        if (fin != 0u) {
+            if (status != MARCH_CONTINUE) {
+                store_march<VAR, NSLOT>(pool, my, m, false);
+                pool.seti(F_STATUS, my, status == MARCH_HIT ? ST_HIT : ST_MISS);
+                pend[n_pend + __popc(fin & lane_lt)] = (uint8_t)my;
+                my = -1;
+            }
+            n_pend += __popc(fin);
+            __syncwarp();
+        }
+    }
+
+    if (VAR::COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cnt.evals += __shfl_xor_sync(kFull, cnt.evals, o);
+            cnt.rays += __shfl_xor_sync(kFull, cnt.rays, o);
+            cnt.normals += __shfl_xor_sync(kFull, cnt.normals, o);
+            cnt.samples += __shfl_xor_sync(kFull, cnt.samples, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&P.counters[0], cnt.evals);
+            atomicAdd(&P.counters[1], cnt.rays);
+            atomicAdd(&P.counters[2], cnt.normals);
+            atomicAdd(&P.counters[3], cnt.samples);
+            atomicAdd(&P.counters[4], c_iters);
+            atomicAdd(&P.counters[5], c_active);
+            atomicAdd(&P.counters[6], c_rounds);
+            atomicAdd(&P.counters[8], c_resolved);
+        }
+    }
+}
+
+
+template <class VAR, int NSLOT>
+__global__ void __launch_bounds__(kPoolBlock, kPoolMinBlocks) k_pathtrace_pool(const __grid_constant__ KParams P)
+{
+    pool_body<VAR, NSLOT>(P);
+}
+
+}  // namespace rt

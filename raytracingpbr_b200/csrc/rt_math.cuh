@@ -12,8 +12,16 @@
 // sin/cos/atan2/asin are the polynomial routines below -- never libdevice/libm, which differ
 // bitwise between host and device.
 #pragma once
+#if defined(__CUDACC_RTC__)
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned char uint8_t;
+typedef unsigned long size_t;
+#else
 #include <cstdint>
 #include <cmath>
+#endif
 
 #if defined(__CUDACC__)
 #define RT_HD __host__ __device__ __forceinline__

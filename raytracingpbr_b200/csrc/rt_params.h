@@ -1,7 +1,9 @@
 // rt_params.h -- kernel parameter block (lives in the constant bank via __grid_constant__).
 #pragma once
+#if !defined(__CUDACC_RTC__)
 #include <cstdint>
 #include <vector_types.h>
+#endif
 
 namespace rt {
 

@@ -1,0 +1,125 @@
+"""Scene-specialised kernels (NVRTC): the generated nearest() must be bit-identical to the generic
+one.  CPU part: the generated function is compiled for the host next to the generic code and
+compared on random points; NVRTC is run on the full translation unit (no GPU needed).  GPU part:
+whole images with the JIT kernel on and off."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+from raytracingpbr_b200 import _native as N, scenes
+
+PRESETS = {
+    "cornell_box_shortest": (scenes.cornell_box_shortest, "Variant<FAMILY_A, 0, SHAPESET_BOX, MARCH_PLAIN, false>", 1.5),
+    "cornell_box": (scenes.cornell_box, "Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_PLAIN, false>", 1.5),
+    "cornell_box_v3": (scenes.cornell_box_v3, "Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_ENHANCED, false>", 15.0),
+    "tokyo_ibl": (scenes.tokyo_ibl, "Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_ENHANCED, false>", 3.0),
+    "bunny_glass": (scenes.bunny_glass, "Variant<FAMILY_B, 0, SHAPESET_BUNNY, MARCH_ENHANCED, false>", 1.2),
+    "src_scene": (scenes.src_scene, "Variant<FAMILY_C, 0, SHAPESET_ANALYTIC, MARCH_SRC, false>", 3.0),
+}
+
+HARNESS = r'''
+#include <cstring>
+#include <vector>
+#include "%(csrc)s/host_setup.h"
+#include "%(csrc)s/rt_integrator.cuh"
+namespace rt {
+%(func)s
+}
+using namespace rt;
+extern "C" __attribute__((visibility("default"))) int jit_check(const RtpbrConfig* cfg, const RtpbrObject* objs, int n, int frame,
+                                                                 const float* pts, int npts, float* out_best, int* out_idx)
+{
+    KParams P;
+    memset(&P, 0, sizeof(P));
+    fill_config(P, *cfg);
+    fill_objects(P, objs, n);
+    fill_frame(P, frame);
+    int bad = 0;
+    for (int k = 0; k < npts; ++k) {
+        vec3 p = V3(pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]);
+        int i0, i1;
+        float a = nearest<%(variant)s>(P, p, i0);
+        float b = jit_nearest(P, p, i1);
+        out_best[k] = b; out_idx[k] = i1;
+        if (memcmp(&a, &b, 4) != 0 || i0 != i1) ++bad;
+    }
+    return bad;
+}
+'''
+
+
+def specialised_function(cfg, objs):
+    src = N.jit_source(cfg, [o.to_native() for o in objs])
+    body = src[src.index("namespace rt {") + len("namespace rt {"):src.index("}  // namespace rt")]
+    assert "jit_nearest" in body
+    return src, body
+
+
+@pytest.mark.parametrize("name", list(PRESETS))
+def test_generated_nearest_is_bit_identical_on_host(name, tmp_path):
+    preset, variant, extent = PRESETS[name]
+    cfg, objs, cam, _ = preset(32, 32)
+    src, body = specialised_function(cfg, objs)
+    csrc = os.path.join(common.ROOT, "raytracingpbr_b200", "csrc")
+    cu = tmp_path / "jit_check.cu"
+    cu.write_text(HARNESS % dict(csrc=csrc, func=body, variant=variant))
+    so = tmp_path / "libjit_check.so"
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Wno-deprecated-gpu-targets", "-Xcompiler",
+                           "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma,-fvisibility=hidden", "-o", str(so), str(cu)],
+                          stderr=subprocess.DEVNULL)
+    L = C.CDLL(str(so))
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform(-extent, extent, (6000, 3)), rng.normal(size=(2000, 3)) * extent * 0.3]).astype(np.float32)
+    pts[:8] = 0.0
+    nat = [o.to_native() for o in objs]
+    arr = (N.RtpbrObject * len(nat))(*nat)
+    best = np.zeros(len(pts), np.float32)
+    idx = np.zeros(len(pts), np.int32)
+    bad = L.jit_check(C.byref(cfg), arr, len(nat), 7, pts.ctypes.data_as(C.POINTER(C.c_float)), len(pts),
+                      best.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int)))
+    assert bad == 0
+    assert len(set(idx.tolist())) >= min(3, len(objs))       # the probe points reach several objects
+
+
+def test_specialised_source_drops_zero_terms():
+    cfg, objs, _, _ = scenes.cornell_box_shortest(32, 32)
+    src, body = specialised_function(cfg, objs)
+    first = body[body.index("object 0"):body.index("object 1")]
+    assert "vec3 p = V3(dx, dy, dz);" in first and "pos.x;" in first        # identity rotation, zero offsets
+    assert "P.geom" not in body                                               # no parameter-block loads in the march loop
+
+
+@pytest.mark.parametrize("name", list(PRESETS))
+def test_nvrtc_compiles_the_specialised_kernel(name):
+    preset = PRESETS[name][0]
+    cfg, objs, _, _ = preset(32, 32)
+    try:
+        N.jit_compile_check(cfg, [o.to_native() for o in objs])
+    except N.RtpbrError as e:
+        if "dlopen" in str(e):
+            pytest.skip("NVRTC not available on this machine")
+        raise
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell_box_shortest", "tokyo_ibl", "src_scene"])
+def test_jit_and_aot_kernels_give_the_same_bits(name):
+    from raytracingpbr_b200 import PathTracer
+    preset = PRESETS[name][0]
+    cfg, objs, cam, tm = preset(96, 64, seed=3, max_bounces=8)
+    out = {}
+    for jit in (True, False):
+        with PathTracer(cfg, objs, cam, tm) as pt:
+            pt.ctx.set_jit(jit)
+            if cfg.sky == N.SKY_ENVMAP:
+                pt.set_envmap(common.env_table(np.random.default_rng(1).integers(0, 256, (16, 8, 3), dtype=np.uint8), 1.4, 2.2))
+            pt.refresh()
+            pt.pathtrace(6)
+            out[jit] = pt.image_buffer.to_numpy()
+            active, msg = pt.ctx.jit_status()
+            assert active == jit, msg
+    assert np.array_equal(out[True], out[False])

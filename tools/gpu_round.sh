@@ -13,6 +13,6 @@ for q in 1 4 8 16 32; do
   RTPBR_RESOLVE_MIN=$q timeout 120 python tools/profile_step.py --passes 4 >> gpurun_out/sweep.log 2>&1
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py --passes 4 > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pathtrace_pool -s 1 -c 1 -o gpurun_out/prof_r01b -f python tools/profile_step.py --passes 2 --spp 16 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pathtrace_pool -s 1 -c 1 -o gpurun_out/prof_r01c -f python tools/profile_step.py --passes 2 --spp 16 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log; cat gpurun_out/bench.json; cat gpurun_out/sweep.log
