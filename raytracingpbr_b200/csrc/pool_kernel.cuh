@@ -109,7 +109,10 @@ __device__ __forceinline__ void pool_body(const KParams& P)
     WorkCounters cnt = { 0, 0, 0, 0 };
     unsigned long long c_iters = 0, c_active = 0, c_rounds = 0, c_resolved = 0;
 
+    bool dirty = true;   // warp-uniform: slots changed hands since the last bookkeeping pass
+    unsigned active = 0u;
     for (;;) {
+      if (dirty) {
         // ---------------------------------------------------------------- acquire ready slots
         const unsigned needy = __ballot_sync(kFull, my < 0);
         if (needy != 0u && n_ready > 0) {
@@ -120,7 +123,7 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             }
             n_ready -= min(__popc(needy), n_ready);
         }
-        const unsigned active = __ballot_sync(kFull, my >= 0);
+        active = __ballot_sync(kFull, my >= 0);
 
         // ---------------------------------------------------------------- resolve phase
         if (active != kFull && n_pend > 0 && (n_pend >= P.resolve_min || active == 0u)) {
@@ -277,6 +280,8 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             continue;
         }
         if (active == 0u) break;   // nothing marching, nothing pending, nothing ready: pool drained
+        dirty = false;
+      }
 
         // ---------------------------------------------------------------- march step
         if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(active); }
@@ -291,6 +296,8 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                 my = -1;
             }
             n_pend += __popc(fin);
+            active &= ~fin;
+            dirty = true;
             __syncwarp();
         }
     }
