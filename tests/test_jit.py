@@ -89,7 +89,7 @@ def test_specialised_source_drops_zero_terms():
     cfg, objs, _, _ = scenes.cornell_box_shortest(32, 32)
     src, body = specialised_function(cfg, objs)
     first = body[body.index("object 0"):body.index("object 1")]
-    assert "vec3 p = V3(dx, dy, dz);" in first and "pos.x;" in first        # identity rotation, zero offsets
+    assert "vec3 p0 = V3(dx0, dy0, dz0);" in first and "pos.x;" in first    # identity rotation, zero offsets
     assert "P.geom" not in body                                               # no parameter-block loads in the march loop
 
 
