@@ -110,21 +110,25 @@ def cpu_sample_columns(width: int, bands: int = 16, cols: int = 2):
 def run_cpu_oracle(spp: int, hoisted: bool, threads: int = 0, bands: int = 16, cols: int = 2):
     """Time the oracle on the sample columns of the C1 image.  Returns (Msamples/s, samples, s)."""
     from oracle import pyoracle as po   # checker / CPU baseline only (never the product path)
+    threads = threads or cpu_threads()
     cfg = po.cornell_shortest_config(W, H, BOUNCES, seed=0)
     objs = po.objects_array(po.cornell_shortest_objects())
     img = np.zeros((W, H, 4), dtype=np.float32)
-    samples = 0
+    columns = [i for (i0, i1) in cpu_sample_columns(W, bands, cols) for i in range(i0, i1)]
+    samples = len(columns) * H * spp
     t0 = time.perf_counter()
-    for (i0, i1) in cpu_sample_columns(W, bands, cols):
-        po.pathtrace(cfg, objs, spp, image_buffer=img, i0=i0, i1=i1, hoisted=hoisted, nthreads=threads)
-        samples += (i1 - i0) * H * spp
+    po.pathtrace_columns(cfg, objs, spp, columns, img, hoisted=hoisted, nthreads=threads)   # one OpenMP region, all threads
     dt = time.perf_counter() - t0
     return samples / dt / 1e6, samples, dt
 
 
 def cpu_threads() -> int:
-    from oracle import pyoracle as po
-    return int(po.lib().orc_max_threads())
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU legs pass
+    this count to the oracle explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def reference_arm(args, rank: int) -> int:
@@ -158,6 +162,62 @@ def reference_arm(args, rank: int) -> int:
     return 0
 
 
+# ------------------------------------------------------------------------------ other configs (informational)
+EXTRA_WORKLOADS = {
+    # name: (preset, width, height, spp, max bounces, (exposure, gamma) of the synthetic environment, description)
+    "c2": ("bunny_glass", 1024, 1024, 256, 16, (1.8, 2.2), "C2: bunny_sdf_glass scene, frame 0, 1024x1024, 256 spp, max 16 bounces"),
+    "c3": ("tokyo_ibl", 1920, 1080, 128, 8, (1.8, 2.2), "C3: tokyo_ibl scene, 1920x1080, 128 spp, max 8 bounces"),
+}
+
+
+def synthetic_env_u8(w=3200, h=1600, seed=11):
+    """Stand-in for the reference's 3200 x 1600 .hdr assets (not redistributable, absent on the GPU box):
+    a smooth sky gradient with a bright sun lobe plus seeded noise, as uint8 (W, H, 3)."""
+    rng = np.random.default_rng(seed)
+    u = np.linspace(0, 1, w, dtype=np.float32)[:, None]
+    v = np.linspace(0, 1, h, dtype=np.float32)[None, :]
+    sky = 60 + 150 * v + 25 * np.sin(6.28 * u)
+    sun = 255 * np.exp(-((u - 0.3) ** 2 + (v - 0.8) ** 2) * 400)
+    img = np.clip(sky + sun, 0, 255)[..., None] * np.array([0.9, 0.95, 1.0], np.float32)
+    img = img + rng.integers(0, 8, size=(w, h, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def extra_workload(args) -> int:
+    """Single-GPU timing of another BASELINE.json config (no CPU leg, no counters); one JSON line."""
+    from raytracingpbr_b200 import PathTracer, ibl, scenes
+    preset, w, h, spp, bounces, env, desc = EXTRA_WORKLOADS[args.workload]
+    cfg, objs, cam, tm = getattr(scenes, preset)(w, h, max_bounces=bounces, seed=0)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.set_envmap(ibl.process(synthetic_env_u8(), *env))
+        ctx = pt.ctx
+
+        def step():
+            ctx.flush_l2()
+            ctx.refresh()
+            ctx.set_sample_base(0)
+            ctx.pathtrace(spp)
+        for _ in range(args.warmup):
+            step()
+        ctx.sync()
+        ctx.kernel_time()
+        sampler = ClockSampler(0)
+        sampler.start()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            step()
+        ms = ctx.timer_stop()
+        clocks = sampler.stop()
+        kernel_ms, launches = ctx.kernel_time()
+        active, jit = ctx.jit_status()
+    line = {"metric": "Msamples/s (pixels x spp / s)", "value": w * h * spp / (ms / args.steps * 1e-3) / 1e6, "unit": UNIT,
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (procedural 3200x1600 environment)",
+            "config": {"workload": desc, "jit": jit}, "kernel_ms_per_step": kernel_ms / args.steps, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def main() -> int:
     ap = argparse.ArgumentParser()
@@ -168,7 +228,11 @@ def main() -> int:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel", default="persistent", choices=["persistent", "simple"])
     ap.add_argument("--counters", action="store_true", help="extra untimed pass with work counters (default at N=1)")
+    ap.add_argument("--workload", default="c1", choices=list(EXTRA_WORKLOADS) + ["c1"],
+                    help="c1 = the headline (default); c2 / c3 = BASELINE.json configs[2] / configs[3], informational")
     args = ap.parse_args()
+    if args.workload != "c1":
+        return extra_workload(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -338,7 +402,7 @@ def main() -> int:
             "config": {"workload": WORKLOAD, "width": W, "height": H, "spp_per_step": spp, "max_bounces": BOUNCES,
                        "sharding": f"{world} x 32-column interleaved bands, spp x {world}" if world > 1 else "none",
                        "l2": "flushed between steps by a 256 MiB memset on the launch stream (inside the timed region)",
-                       "kernel": args.kernel, "blocks_per_sm": info["blocks_per_sm"]},
+                       "kernel": args.kernel, "blocks_per_sm": info["blocks_per_sm"], "jit": ctx.jit_status()[1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "alpha_checksum": checksum},
             "gpu_launches": launches,

@@ -86,6 +86,9 @@ def lib() -> C.CDLL:
         L.orc_pathtrace_ex.restype = C.c_int
         L.orc_pathtrace_ex.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, f32p, f32p, C.c_int, C.c_int,
                                        C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OrcCounters)]
+        L.orc_pathtrace_cols.restype = C.c_int
+        L.orc_pathtrace_cols.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, C.c_int, C.c_uint32,
+                                         C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]
         L.orc_signed_distance_g.restype = C.c_float
         L.orc_signed_distance_g.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, C.c_int, f32p]
         L.orc_nearest_g.restype = C.c_int
@@ -235,4 +238,16 @@ def pathtrace(cfg: OrcConfig, objs, spp: int, sample_base: int = 0, image_buffer
         raise RuntimeError(f"orc_pathtrace_ex failed: {rc}")
     if counters:
         return image_buffer, {k: getattr(cnt, k) for k, _ in OrcCounters._fields_}
+    return image_buffer
+
+
+def pathtrace_columns(cfg: OrcConfig, objs, spp: int, columns, image_buffer: np.ndarray, hoisted: bool = True,
+                      nthreads: int = 0, sample_base: int = 0) -> np.ndarray:
+    """Families A/B on an explicit list of columns, one parallel region (bench.py's bounded CPU sample)."""
+    arr = objs if isinstance(objs, C.Array) else objects_array(objs)
+    cols = (C.c_int * len(columns))(*[int(c) for c in columns])
+    rc = lib().orc_pathtrace_cols(C.byref(cfg), arr, len(arr), _f32p(image_buffer), spp, sample_base, cols, len(columns),
+                                  int(hoisted), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"orc_pathtrace_cols failed: {rc}")
     return image_buffer
