@@ -8,8 +8,8 @@ examples/cornell_box/cornell_box_shortest.py, 1024 x 1024, 64 spp, max 8 bounces
 one pass of the hot path over that batch: refresh() + pathtrace(spp) (+ the NCCL tile reduce
 when N > 1).  Metric: Msamples/s = pixels x spp / seconds.
 
-N > 1 (launched by torchrun, one process per GPU): the image is sharded by 32-column bands
-(rank = (i / 32) mod N) and the spp is scaled by N, so every GPU traces the same number of
+N > 1 (launched by torchrun, one process per GPU): the image is sharded by 4-column bands
+(rank = (i / 4) mod N) and the spp is scaled by N, so every GPU traces the same number of
 samples as at N = 1 (weak scaling); the only collective is the NCCL sum of per-tile sample
 sums at the end of the step (tonemap time).  torch.distributed is used for the barrier, the
 max-over-ranks reduction of the timings and the NCCL-id broadcast only.
@@ -46,6 +46,7 @@ METRIC = "Msamples/s (pixels x spp / s), Cornell Box 1024^2, 8 bounces"
 UNIT = "Msamples/s"
 W, H, SPP, BOUNCES = 1024, 1024, 64, 8
 WORKLOAD = "C1: cornell_box_shortest scene, 1024x1024, 64 spp, max 8 bounces"
+BAND = 4                                 # N > 1: rank = (column / BAND) mod N -- fine interleave balances the ranks
 # bytes / flops per unit
 BYTES_PER_SAMPLE = 16                    # pool kernel: one float4 (radiance, 1) per sample into the scratch buffer
 BYTES_PER_PIXEL_PER_LAUNCH = 32          # simple kernel: vec4 f32 accumulator, 16 B read + 16 B write
@@ -278,7 +279,7 @@ def main() -> int:
     ctx = pt.ctx
     if world > 1:
         import torch
-        ctx.set_shard(rank, world, 32)
+        ctx.set_shard(rank, world, BAND)
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid = torch.frombuffer(bytearray(N.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
@@ -400,7 +401,7 @@ def main() -> int:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "spp_per_step": spp, "max_bounces": BOUNCES,
-                       "sharding": f"{world} x 32-column interleaved bands, spp x {world}" if world > 1 else "none",
+                       "sharding": f"{world} ranks, {BAND}-column interleaved bands, spp x {world}" if world > 1 else "none",
                        "l2": "flushed between steps by a 256 MiB memset on the launch stream (inside the timed region)",
                        "kernel": args.kernel, "blocks_per_sm": info["blocks_per_sm"], "jit": ctx.jit_status()[1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -121,5 +121,7 @@ def test_jit_and_aot_kernels_give_the_same_bits(name):
             pt.pathtrace(6)
             out[jit] = pt.image_buffer.to_numpy()
             active, msg = pt.ctx.jit_status()
+            if jit and not active and "dlopen" in msg:
+                pytest.skip("NVRTC not available on this machine: " + msg)
             assert active == jit, msg
     assert np.array_equal(out[True], out[False])
