@@ -326,10 +326,12 @@ __device__ __forceinline__ void pool_body(const KParams& P)
 
 // The neural bunny keeps ~50 floats live per SDF evaluation: give it 128 registers (2 CTAs / SM).
 template <class VAR>
-constexpr int pool_min_blocks() { return VAR::SHAPESET == SHAPESET_BUNNY ? 2 : kPoolMinBlocks; }
+struct PoolLaunch {
+    static constexpr int kMinBlocks = VAR::SHAPESET == SHAPESET_BUNNY ? 2 : kPoolMinBlocks;
+};
 
 template <class VAR, int NSLOT>
-__global__ void __launch_bounds__(kPoolBlock, pool_min_blocks<VAR>()) k_pathtrace_pool(const __grid_constant__ KParams P)
+__global__ void __launch_bounds__(kPoolBlock, PoolLaunch<VAR>::kMinBlocks) k_pathtrace_pool(const __grid_constant__ KParams P)
 {
     pool_body<VAR, NSLOT>(P);
 }
