@@ -50,6 +50,9 @@ BAND = 4                                 # N > 1: rank = (column / BAND) mod N -
 # bytes / flops per unit
 BYTES_PER_SAMPLE = 16                    # pool kernel: one float4 (radiance, 1) per sample into the scratch buffer
 BYTES_PER_PIXEL_PER_LAUNCH = 32          # simple kernel: vec4 f32 accumulator, 16 B read + 16 B write
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_pathtrace_pool_jit launch at the C1 configuration
+# (ncu --set full, profiles/r01d_ncu_full_k_pathtrace_pool_jit_c1.csv: 66.57 MB read + 1067.82 MB written)
+NCU_TRAFFIC_BYTES_C1 = 66.570240e6 + 1.067819e9
 FLOP_PER_SCENE_EVAL = 8 * 41             # 8 boxes x 41 flop
 FLOP_PER_NORMAL = 4 * 41
 FLOP_PER_RAY_SHADE = 150
@@ -359,7 +362,9 @@ def main() -> int:
                  else BYTES_PER_PIXEL_PER_LAUNCH * local_pixels)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "k_pathtrace_pool" if kernel == N.KERNEL_PERSISTENT else "k_pathtrace_simple",
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": NCU_TRAFFIC_BYTES_C1 if (kernel == N.KERNEL_PERSISTENT and world == 1) else None,
+            "algorithmic_bytes_per_launch": alg_bytes,
             "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "kernel_share_of_step": kernel_ms_max / ms,
             "note": "this path is instruction-issue bound, not HBM bound (16 B written per sample); see fp32"}
 
