@@ -135,7 +135,9 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             }
             n_ready += __popc(active);
             __syncwarp();
-            while (n_pend > 0) {
+            // One batch always; further batches only while they are full.  A small remainder stays on
+            // the pending stack for the next round instead of costing a whole 32-wide pass.
+            do {
                 const int take = min(n_pend, 32);
                 const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
                 n_pend -= take;
@@ -276,7 +278,7 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                 if (slot >= 0 && st == ST_READY) ready[n_ready + __popc(rdy & lane_lt)] = (uint8_t)slot;
                 n_ready += __popc(rdy);
                 __syncwarp();
-            }
+            } while (n_pend >= 32);
             continue;
         }
         if (active == 0u) break;   // nothing marching, nothing pending, nothing ready: pool drained
