@@ -152,3 +152,79 @@ def test_error_behaviour():
     with pytest.raises(RtpbrError) as e:
         N.Context(bad)
     assert e.value.code == N.ERR_ARG
+
+
+# ------------------------------------------------------------------ BASELINE.json configs[2..4] at full resolution
+def _render_preset(preset, w, h, spp, kernel, env=None, frame=None, jit=True, **kw):
+    cfg, objs, cam, tm = preset(w, h, seed=0, kernel=kernel, **kw)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.ctx.set_jit(jit)
+        if env is not None:
+            pt.set_envmap(env)
+        if frame is not None:
+            pt.ctx.set_frame(frame)
+        pt.refresh()
+        pt.pathtrace(spp)
+        return pt.image_buffer.to_numpy()
+
+
+def _synthetic_env(w=256, h=128, seed=2):
+    u8 = np.random.default_rng(seed).integers(0, 256, (w, h, 3), dtype=np.uint8)
+    return common.env_table(u8, 1.8, 2.2)
+
+
+def test_c3_tokyo_full_resolution_kernels_agree():
+    # configs[3]: 1920 x 1080, 8 bounces (spp reduced: the property is size-independent)
+    env = _synthetic_env()
+    a = _render_preset(scenes.tokyo_ibl, 1920, 1080, 4, N.KERNEL_PERSISTENT, env=env, max_bounces=8)
+    assert (a[..., 3] == 4.0).all() and np.isfinite(a).all()
+    b = _render_preset(scenes.tokyo_ibl, 1920, 1080, 4, N.KERNEL_SIMPLE, env=env, max_bounces=8)
+    assert np.array_equal(a, b)
+    c = _render_preset(scenes.tokyo_ibl, 1920, 1080, 4, N.KERNEL_PERSISTENT, env=env, max_bounces=8, jit=False)
+    assert np.array_equal(a, c)
+    # oracle on two columns
+    cfg, objs, cam, _ = scenes.tokyo_ibl(1920, 1080, max_bounces=8, seed=0)
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    for i0 in (7, 960):
+        want = po.pathtrace(oc, oo, 4, env=env, i0=i0, i1=i0 + 1)
+        assert np.array_equal(a[i0], want[i0]), i0
+
+
+def test_c2_bunny_full_resolution_kernels_agree():
+    # configs[2]: 1024 x 1024, 16 bounces, frame 0 (spp reduced)
+    env = _synthetic_env(seed=4)
+    a = _render_preset(scenes.bunny_glass, 1024, 1024, 2, N.KERNEL_PERSISTENT, env=env, frame=0, max_bounces=16)
+    assert (a[..., 3] == 2.0).all() and np.isfinite(a).all()
+    b = _render_preset(scenes.bunny_glass, 1024, 1024, 2, N.KERNEL_SIMPLE, env=env, frame=0, max_bounces=16)
+    assert np.array_equal(a, b)
+    cfg, objs, cam, _ = scenes.bunny_glass(1024, 1024, max_bounces=16, seed=0, frame=0)
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    want = po.pathtrace(oc, oo, 2, env=env, i0=500, i1=501)
+    assert np.array_equal(a[500], want[500])
+
+
+def test_c4_resolution_4096_sharded_property():
+    # configs[4]: 4096 x 4096 tile-sharded over 8 ranks; here one GPU renders shard 3 of 8 and a 1-rank crop check
+    part = render(4096, 4096, 1, 8, shard=(3, 8, 4))
+    own = ((np.arange(4096) // 4) % 8) == 3
+    assert (part[~own] == 0).all() and (part[own][..., 3] == 1.0).all()
+    want = oracle(4096, 4096, 1, 8, i0=12, i1=16)       # columns 12..15 belong to rank 3
+    assert np.array_equal(part[12:16], want[12:16])
+
+
+def test_src_progressive_alpha_counts_paths():
+    # family C: image_buffer.a counts finished paths (differs per pixel); Msamples must use sum(alpha)
+    cfg, objs, cam, tm = scenes.src_scene(256, 144, seed=2)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.set_envmap(_synthetic_env(seed=6))
+        pt.refresh()
+        pt.pathtrace(64)
+        buf = pt.image_buffer.to_numpy()
+        rb = pt.ray_buffer.to_numpy()
+    alpha = buf[..., 3]
+    assert alpha.min() >= 1 and alpha.max() <= 64 and alpha.std() > 0
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    orb = np.zeros((256, 144, 10), np.float32)
+    want = po.pathtrace(oc, oo, 64, env=_synthetic_env(seed=6), ray_buffer=orb, i0=100, i1=102)
+    assert np.array_equal(buf[100:102], want[100:102])
+    assert np.array_equal(rb[100:102].view(np.int32), orb[100:102].view(np.int32))
