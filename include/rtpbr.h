@@ -117,6 +117,9 @@ typedef struct RtpbrConfig {
     int32_t normal_mode;          /* 0: world-space tetrahedron offsets (shortest:55-61);
                                      1: object-space, one transform (src/sdf.py:77-87) */
     int32_t samples_per_pixel;    /* SAMPLES_PER_PIXEL per launch, src/config.py:10 (family C) */
+    int32_t adaptive_sampling;    /* ADAPTIVE_SAMPLING, src/config.py:14 (family C): pathtrace() skips pixels whose running
+                                     mean of tone-mapped change, diff_pixels, is <= noise_threshold (src/pathtracer.py:97-101) */
+    float noise_threshold;        /* NOISE_THRESHOLD, src/config.py:17 */
     int32_t kernel;               /* RTPBR_KERNEL_* */
     int32_t count_work;           /* 1: count scene evals / rays / lane occupancy (slower) */
 } RtpbrConfig;
@@ -126,7 +129,9 @@ typedef struct RtpbrContext RtpbrContext;
 /* which-buffer selectors for rtpbr_download / rtpbr_upload */
 enum { RTPBR_BUF_IMAGE_BUFFER = 0,  /* image_buffer  vec4 f32 (W,H,4), src/fileds.py:8 */
        RTPBR_BUF_IMAGE_PIXELS = 1,  /* image_pixels  vec3 f32 (W,H,3), src/fileds.py:9 */
-       RTPBR_BUF_RAY_BUFFER = 2 };  /* ray_buffer    AOS Ray, 10 x 4 bytes (W,H,10), src/fileds.py:7 */
+       RTPBR_BUF_RAY_BUFFER = 2,    /* ray_buffer    AOS Ray, 10 x 4 bytes (W,H,10), src/fileds.py:7 */
+       RTPBR_BUF_DIFF_BUFFER = 3,   /* diff_buffer   vec2 f32 (W,H,2), src/fileds.py:21 (adaptive sampling only) */
+       RTPBR_BUF_DIFF_PIXELS = 4 }; /* diff_pixels   f32 (W,H,1), src/fileds.py:22 (adaptive sampling only) */
 
 /* counters written by rtpbr_get_counters (valid when count_work = 1) */
 enum { RTPBR_CNT_SCENE_EVALS = 0, RTPBR_CNT_RAYS = 1, RTPBR_CNT_NORMALS = 2, RTPBR_CNT_SAMPLES = 3,
@@ -163,7 +168,8 @@ RTPBR_API int rtpbr_refresh(RtpbrContext* ctx);
 RTPBR_API int rtpbr_pathtrace(RtpbrContext* ctx, int spp);
 /* replaces kernel post_process() (src/postprocessor.py:24-43) / the tonemap tail of render()
  * (cornell_box_shortest.py:124-129).  mode: 0 family A, 1 family B, 2 family C, 3 v3. */
-RTPBR_API int rtpbr_post_process(RtpbrContext* ctx, int mode, float exposure, float gamma);
+RTPBR_API int rtpbr_post_process(RtpbrContext* ctx, int mode, float exposure, double gamma);  /* gamma in binary64: the
+   reference folds 1.0 / camera_gamma in Python before casting to f32 (src/postprocessor.py:32) */
 
 /* replaces field.to_numpy() / canvas.set_image(field) / ti.tools.imwrite(field) reads */
 RTPBR_API int rtpbr_download(RtpbrContext* ctx, int which, void* host, size_t bytes);

@@ -56,6 +56,7 @@ class OrcConfig(C.Structure):
         ("min_dis", C.c_float), ("pixel_radius", C.c_float), ("quality_per_sample", C.c_float),
         ("black_background", C.c_int32),
         ("nearest_seed", C.c_int32), ("normal_mode", C.c_int32), ("samples_per_pixel", C.c_int32),
+        ("adaptive_sampling", C.c_int32), ("noise_threshold", C.c_float),
     ]
 
 
@@ -86,6 +87,11 @@ def lib() -> C.CDLL:
         L.orc_pathtrace_ex.restype = C.c_int
         L.orc_pathtrace_ex.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, f32p, f32p, C.c_int, C.c_int,
                                        C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OrcCounters)]
+        L.orc_pathtrace_adaptive.restype = C.c_int
+        L.orc_pathtrace_adaptive.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, f32p, f32p, f32p, C.c_int,
+                                             C.c_int, C.c_int, C.c_uint32, C.c_int]
+        L.orc_post_process_src.restype = None
+        L.orc_post_process_src.argtypes = [C.c_int, f32p, f32p, f32p, f32p, C.c_float, C.c_double, C.c_int]
         L.orc_pathtrace_cols.restype = C.c_int
         L.orc_pathtrace_cols.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcObject), C.c_int, f32p, C.c_int, C.c_uint32,
                                          C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]
@@ -209,6 +215,7 @@ def cornell_shortest_config(width=512, height=512, max_bounces=3, seed=0) -> Orc
     c.frame = 0
     c.min_dis, c.pixel_radius, c.quality_per_sample, c.black_background = 0.0, 0.0, 0.8, 0
     c.nearest_seed, c.normal_mode, c.samples_per_pixel = 0, 0, 1
+    c.adaptive_sampling, c.noise_threshold = 0, 1e-4
     return c
 
 
@@ -251,3 +258,20 @@ def pathtrace_columns(cfg: OrcConfig, objs, spp: int, columns, image_buffer: np.
     if rc != 0:
         raise RuntimeError(f"orc_pathtrace_cols failed: {rc}")
     return image_buffer
+
+
+def pathtrace_adaptive(cfg: OrcConfig, objs, launches: int, image_buffer, ray_buffer, diff_pixels, env, sample_base: int = 0):
+    """Family C with ADAPTIVE_SAMPLING: `launches` x kernel pathtrace() reading the diff_pixels field."""
+    arr = objs if isinstance(objs, C.Array) else objects_array(objs)
+    rc = lib().orc_pathtrace_adaptive(C.byref(cfg), arr, len(arr), _f32p(image_buffer), _f32p(ray_buffer), _f32p(diff_pixels),
+                                      _f32p(env) if env is not None else None, env.shape[0] if env is not None else 0,
+                                      env.shape[1] if env is not None else 0, launches, sample_base, 0)
+    if rc != 0:
+        raise RuntimeError(f"orc_pathtrace_adaptive failed: {rc}")
+
+
+def post_process_src(image_buffer, image_pixels, diff_buffer, diff_pixels, exposure: float, gamma: float, adaptive: bool):
+    """kernel post_process() of src/postprocessor.py:24-43, in place on image_pixels / diff_*."""
+    n = image_buffer.shape[0] * image_buffer.shape[1]
+    lib().orc_post_process_src(n, _f32p(image_buffer), _f32p(image_pixels), _f32p(diff_buffer), _f32p(diff_pixels),
+                               exposure, gamma, int(adaptive))

@@ -23,7 +23,7 @@ FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2
 MARCH_PLAIN, MARCH_ENHANCED, MARCH_SRC = 0, 1, 2
 SKY_BLACK, SKY_ENVMAP, SKY_GRADIENT = 0, 1, 2
 KERNEL_PERSISTENT, KERNEL_SIMPLE = 0, 1
-BUF_IMAGE_BUFFER, BUF_IMAGE_PIXELS, BUF_RAY_BUFFER = 0, 1, 2
+BUF_IMAGE_BUFFER, BUF_IMAGE_PIXELS, BUF_RAY_BUFFER, BUF_DIFF_BUFFER, BUF_DIFF_PIXELS = 0, 1, 2, 3, 4
 CNT_NAMES = ("scene_evals", "rays", "normals", "samples", "march_iters", "march_active", "resolve_rounds", "launches",
              "resolved_slots", "reserved")
 
@@ -73,6 +73,7 @@ class RtpbrConfig(C.Structure):
         ("min_dis", C.c_float), ("pixel_radius", C.c_float), ("quality_per_sample", C.c_float),
         ("black_background", C.c_int32),
         ("nearest_seed", C.c_int32), ("normal_mode", C.c_int32), ("samples_per_pixel", C.c_int32),
+        ("adaptive_sampling", C.c_int32), ("noise_threshold", C.c_float),
         ("kernel", C.c_int32), ("count_work", C.c_int32),
     ]
 
@@ -113,7 +114,7 @@ def lib() -> C.CDLL:
         "rtpbr_set_shard": [vp, C.c_int, C.c_int, C.c_int],
         "rtpbr_refresh": [vp],
         "rtpbr_pathtrace": [vp, C.c_int],
-        "rtpbr_post_process": [vp, C.c_int, C.c_float, C.c_float],
+        "rtpbr_post_process": [vp, C.c_int, C.c_float, C.c_double],
         "rtpbr_download": [vp, C.c_int, vp, C.c_size_t],
         "rtpbr_upload": [vp, C.c_int, vp, C.c_size_t],
         "rtpbr_sync": [vp],
@@ -281,7 +282,7 @@ class Context:
 
     # -- data -------------------------------------------------------------------------
     def download(self, which: int = BUF_IMAGE_BUFFER, out: np.ndarray | None = None) -> np.ndarray:
-        ch = {BUF_IMAGE_BUFFER: 4, BUF_IMAGE_PIXELS: 3, BUF_RAY_BUFFER: 10}[which]
+        ch = {BUF_IMAGE_BUFFER: 4, BUF_IMAGE_PIXELS: 3, BUF_RAY_BUFFER: 10, BUF_DIFF_BUFFER: 2, BUF_DIFF_PIXELS: 1}[which]
         if out is None:
             out = np.empty((self.width, self.height, ch), dtype=np.float32)
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.width, self.height, ch)

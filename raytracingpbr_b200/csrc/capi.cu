@@ -85,6 +85,8 @@ struct RtpbrContext {
     float4* d_image_buffer = nullptr;
     float* d_image_pixels = nullptr;
     float* d_ray_buffer = nullptr;
+    float* d_diff_buffer = nullptr;   // adaptive sampling (family C): vec2 per pixel
+    float* d_diff_pixels = nullptr;   // adaptive sampling: f32 per pixel
     float* d_rr = nullptr;
     float* d_env = nullptr;
     unsigned long long* d_work = nullptr;
@@ -207,6 +209,12 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     if (cfg->family == RTPBR_FAMILY_C) {   // ray_buffer = Ray.field(), zero-initialised like a fresh Taichi field
         CREATE_TRY(cudaMalloc(&c->d_ray_buffer, n * 10 * sizeof(float)));
         CREATE_TRY(cudaMemsetAsync(c->d_ray_buffer, 0, n * 10 * sizeof(float), c->stream));
+        if (cfg->adaptive_sampling) {   // fresh Taichi fields are zero: nothing is sampled before the first refresh()
+            CREATE_TRY(cudaMalloc(&c->d_diff_buffer, n * 2 * sizeof(float)));
+            CREATE_TRY(cudaMalloc(&c->d_diff_pixels, n * sizeof(float)));
+            CREATE_TRY(cudaMemsetAsync(c->d_diff_buffer, 0, n * 2 * sizeof(float), c->stream));
+            CREATE_TRY(cudaMemsetAsync(c->d_diff_pixels, 0, n * sizeof(float), c->stream));
+        }
     }
     CREATE_TRY(cudaMemsetAsync(c->d_counters, 0, RTPBR_CNT_COUNT * sizeof(unsigned long long), c->stream));
     std::vector<float> rr = rt::rr_table(c->cfg);
@@ -216,6 +224,7 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
 #undef CREATE_TRY
     c->P.image_buffer = c->d_image_buffer;
     c->P.ray_buffer = c->d_ray_buffer;
+    c->P.diff_pixels = c->d_diff_pixels;
     c->P.rr_prob = c->d_rr;
     c->P.env = nullptr;
     c->P.env_w = c->P.env_h = 0;
@@ -237,6 +246,8 @@ int rtpbr_destroy(RtpbrContext* c)
     cudaFree(c->d_image_buffer);
     cudaFree(c->d_image_pixels);
     cudaFree(c->d_ray_buffer);
+    cudaFree(c->d_diff_buffer);
+    cudaFree(c->d_diff_pixels);
     cudaFree(c->d_rr);
     cudaFree(c->d_env);
     cudaFree(c->d_work);
@@ -327,6 +338,7 @@ int rtpbr_refresh(RtpbrContext* c)
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemsetAsync(c->d_image_buffer, 0, npixels(c) * sizeof(float4), c->stream));
     if (c->d_ray_buffer) CUDA_TRY(rt::launch_refresh_depth(c->d_ray_buffer, (int)npixels(c), c->stream));
+    if (c->d_diff_buffer) CUDA_TRY(rt::launch_refresh_adaptive(c->d_diff_buffer, c->d_diff_pixels, (int)npixels(c), c->stream));
     return RTPBR_OK;
 }
 
@@ -472,13 +484,19 @@ int rtpbr_pathtrace(RtpbrContext* c, int spp)
     return RTPBR_OK;
 }
 
-int rtpbr_post_process(RtpbrContext* c, int mode, float exposure, float gamma)
+int rtpbr_post_process(RtpbrContext* c, int mode, float exposure, double gamma)
 {
     if (!c) return fail(RTPBR_ERR_ARG, "null context");
-    if (mode < 0 || mode > 3 || !(gamma > 0.f)) return fail(RTPBR_ERR_ARG, "bad tonemap arguments");
+    if (mode < 0 || mode > 3 || !(gamma > 0.0)) return fail(RTPBR_ERR_ARG, "bad tonemap arguments");
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->cfg.family == RTPBR_FAMILY_C && mode == 2) {
+        // src/postprocessor.py:24-43 under the fp32 contract (feeds adaptive sampling)
+        CUDA_TRY(rt::launch_post_process_src(c->d_image_buffer, c->d_image_pixels, c->d_diff_buffer, c->d_diff_pixels,
+                                             (int)npixels(c), exposure, (float)(1.0 / gamma), c->stream));
+        return RTPBR_OK;
+    }
     CUDA_TRY(rt::launch_post_process(c->d_image_buffer, c->d_image_pixels, (int)npixels(c), mode, exposure,
-                                     (float)(1.0 / (double)gamma), c->stream));
+                                     (float)(1.0 / gamma), c->stream));
     return RTPBR_OK;
 }
 
@@ -490,6 +508,12 @@ static int buffer_of(RtpbrContext* c, int which, void** ptr, size_t* bytes)
     case RTPBR_BUF_RAY_BUFFER:
         if (!c->d_ray_buffer) return fail(RTPBR_ERR_STATE, "ray_buffer exists in family C only");
         *ptr = c->d_ray_buffer; *bytes = npixels(c) * 10 * sizeof(float); return RTPBR_OK;
+    case RTPBR_BUF_DIFF_BUFFER:
+        if (!c->d_diff_buffer) return fail(RTPBR_ERR_STATE, "diff_buffer exists with adaptive_sampling only");
+        *ptr = c->d_diff_buffer; *bytes = npixels(c) * 2 * sizeof(float); return RTPBR_OK;
+    case RTPBR_BUF_DIFF_PIXELS:
+        if (!c->d_diff_pixels) return fail(RTPBR_ERR_STATE, "diff_pixels exists with adaptive_sampling only");
+        *ptr = c->d_diff_pixels; *bytes = npixels(c) * sizeof(float); return RTPBR_OK;
     default: return fail(RTPBR_ERR_ARG, "unknown buffer");
     }
 }

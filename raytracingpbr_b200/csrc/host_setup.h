@@ -121,6 +121,8 @@ inline void fill_config(KParams& P, const RtpbrConfig& c)
     P.bsdf = c.bsdf; P.f0_variant = c.f0_variant;
     P.nearest_seed = c.nearest_seed; P.normal_mode = c.normal_mode;
     P.samples_per_pixel = c.samples_per_pixel > 0 ? c.samples_per_pixel : 1;
+    P.adaptive = c.family == RTPBR_FAMILY_C && c.adaptive_sampling != 0;
+    P.noise_threshold = c.noise_threshold;
     P.inv_max_bounces = (float)(1.0 / (double)c.max_bounces);   // ti.static(1.0 / MAX_RAYTRACE), src/pathtracer.py:68
     P.sky = c.sky; P.sky_scale = c.sky_scale;
     P.min_dis = c.min_dis; P.pixel_radius = c.pixel_radius; P.quality_per_sample = c.quality_per_sample;

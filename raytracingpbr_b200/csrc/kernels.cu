@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kSimpleBlock) k_pathtrace_simple(const __grid_
     int i, j;
     if (w >= P.total_work || !work_to_pixel(P, w, i, j)) return;
     const uint32_t pixel = (uint32_t)(i * P.height + j);
+    if (VAR::FAMILY == FAMILY_C && P.adaptive && !(P.diff_pixels[pixel] > P.noise_threshold)) return;   // src/pathtracer.py:97-101
     float4 acc = P.image_buffer[pixel];
     WorkCounters cnt = { 0, 0, 0, 0 };
     if (VAR::FAMILY == FAMILY_C) {
@@ -133,6 +134,53 @@ __global__ void __launch_bounds__(256) k_post_process(const float4* __restrict__
     image_pixels[3 * p + 2] = c.z;
 }
 
+// kernel post_process() of the src/ package (src/postprocessor.py:24-43, src/aces.py:5-30) under the fp32
+// contract -- matrix products as fmaf chains, pow in binary64 rounded once -- because with
+// ADAPTIVE_SAMPLING its output feeds back into which pixels pathtrace() samples.
+__device__ __forceinline__ float pow_contract(float x, float e) { return (float)pow((double)x, (double)e); }
+__global__ void __launch_bounds__(256) k_post_process_src(const float4* __restrict__ image_buffer, float* __restrict__ image_pixels,
+                                                          float2* __restrict__ diff_buffer, float* __restrict__ diff_pixels, int n,
+                                                          float exposure, float gamma_inv)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float Min[9] = { 0.59719f, 0.35458f, 0.04823f, 0.07600f, 0.90834f, 0.01566f, 0.02840f, 0.13383f, 0.83777f };
+    const float Mout[9] = { 1.60475f, -0.53108f, -0.07367f, -0.10208f, 1.10813f, -0.00605f, -0.00327f, -0.07276f, 1.07602f };
+    const float4 b = image_buffer[p];
+    const vec3 last = V3(image_pixels[3 * p], image_pixels[3 * p + 1], image_pixels[3 * p + 2]);
+    vec3 c = V3(b.x / b.w, b.y / b.w, b.z / b.w);
+    c = c * exposure;
+    c = V3(pow_contract(c.x, gamma_inv), pow_contract(c.y, gamma_inv), pow_contract(c.z, gamma_inv));
+    c = mat_mul(Min, c);
+    {
+        vec3 a = V3(c.x * (c.x + 0.0245786f) - 0.000090537f, c.y * (c.y + 0.0245786f) - 0.000090537f,
+                    c.z * (c.z + 0.0245786f) - 0.000090537f);
+        vec3 d = V3(c.x * (0.983729f * c.x + 0.4329510f) + 0.238081f, c.y * (0.983729f * c.y + 0.4329510f) + 0.238081f,
+                    c.z * (0.983729f * c.z + 0.4329510f) + 0.238081f);
+        c = V3(a.x / d.x, a.y / d.y, a.z / d.z);
+    }
+    c = mat_mul(Mout, c);
+    c = V3(fminf(fmaxf(c.x, 0.f), 1.f), fminf(fmaxf(c.y, 0.f), 1.f), fminf(fmaxf(c.z, 0.f), 1.f));
+    image_pixels[3 * p] = c.x; image_pixels[3 * p + 1] = c.y; image_pixels[3 * p + 2] = c.z;
+    if (diff_buffer != nullptr) {
+        const vec3 dc = V3(fabsf(c.x - last.x), fabsf(c.y - last.y), fabsf(c.z - last.z));
+        float2 db = diff_buffer[p];
+        db.x += brightness(dc);
+        db.y += 1.0f;
+        diff_buffer[p] = db;
+        diff_pixels[p] = db.x / db.y;
+    }
+}
+
+// refresh() with ADAPTIVE_SAMPLING: diff_buffer = vec2(1), diff_pixels = 1e32 (src/renderer.py:18-20)
+__global__ void __launch_bounds__(256) k_refresh_adaptive(float2* diff_buffer, float* diff_pixels, int n)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    diff_buffer[p] = make_float2(1.0f, 1.0f);
+    diff_pixels[p] = 1e32f;
+}
+
 // ------------------------------------------------------------------------------------------
 // Host-side launchers (called from capi.cu)
 // ------------------------------------------------------------------------------------------
@@ -221,6 +269,18 @@ cudaError_t launch_fold_samples(const KParams& P, cudaStream_t stream)
 cudaError_t launch_refresh_depth(float* ray_buffer, int n, cudaStream_t stream)
 {
     k_refresh_depth<<<(n + 255) / 256, 256, 0, stream>>>(ray_buffer, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_post_process_src(const float4* image_buffer, float* image_pixels, float* diff_buffer, float* diff_pixels, int n,
+                                    float exposure, float gamma_inv, cudaStream_t stream)
+{
+    k_post_process_src<<<(n + 255) / 256, 256, 0, stream>>>(image_buffer, image_pixels, reinterpret_cast<float2*>(diff_buffer),
+                                                             diff_pixels, n, exposure, gamma_inv);
+    return cudaGetLastError();
+}
+cudaError_t launch_refresh_adaptive(float* diff_buffer, float* diff_pixels, int n, cudaStream_t stream)
+{
+    k_refresh_adaptive<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<float2*>(diff_buffer), diff_pixels, n);
     return cudaGetLastError();
 }
 cudaError_t launch_post_process(const float4* image_buffer, float* image_pixels, int n, int mode, float exposure,

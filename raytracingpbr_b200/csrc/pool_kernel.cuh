@@ -221,7 +221,9 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                             if (VAR::FAMILY == FAMILY_C) {          // work item = pixel
                                 if (wk >= (unsigned long long)P.total_work) {
                                     st = ST_DEAD;
-                                } else if (work_to_pixel(P, (uint32_t)wk, pi, pj)) {
+                                } else if (work_to_pixel(P, (uint32_t)wk, pi, pj) &&
+                                           // src/pathtracer.py:97-101: if diff > NOISE_THRESHOLD: sample(i, j)
+                                           (!P.adaptive || P.diff_pixels[pi * P.height + pj] > P.noise_threshold)) {
                                     pixel = (uint32_t)(pi * P.height + pj);
                                     acc = P.image_buffer[pixel];
                                     samp = 0;

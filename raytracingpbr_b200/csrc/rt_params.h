@@ -55,6 +55,8 @@ struct KParams {
     float inv_max_bounces;   // float(1.0 / MAX_RAYTRACE), src/pathtracer.py:68
     int32_t black_background;
     int32_t nearest_seed, normal_mode, samples_per_pixel;
+    int32_t adaptive;        // ADAPTIVE_SAMPLING (family C): skip pixels with diff_pixels <= noise_threshold
+    float noise_threshold;
     int32_t frame;
     float anim_m[9];         // bunny programmatic animation: angle(vec3(0, 0, t)), bunny_sdf_glass.py:214
     float anim_bob;          // 0.1 * sin(t), :215
@@ -74,6 +76,7 @@ struct KParams {
     const float* rr_prob;           // [max_bounces] Russian-roulette table (families A/B)
     const float* env;               // (env_w, env_h, 3) or nullptr
     int32_t env_w, env_h;
+    const float* diff_pixels;       // family C adaptive sampling: (W,H) f32, src/fileds.py:22
     float4* scratch;                // families A/B: per-sample radiance, [total_work][spp] (pool kernel -> k_fold_samples)
     unsigned long long* work_counter;   // persistent-kernel work queue head
     unsigned long long* counters;   // RTPBR_CNT_* (count_work builds)

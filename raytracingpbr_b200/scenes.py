@@ -52,6 +52,7 @@ def cornell_box_shortest(width: int = 512, height: int = 512, max_bounces: int =
     c.seed = seed
     c.min_dis, c.pixel_radius, c.quality_per_sample, c.black_background = 0.0, 0.0, 0.8, 0
     c.nearest_seed, c.normal_mode, c.samples_per_pixel = 0, 0, 1
+    c.adaptive_sampling, c.noise_threshold = 0, 1e-4
     c.kernel = kernel
     c.count_work = int(count_work)
     camera = Camera(vec3(0, 0, 3.5), vec3(0, 0, -1), vec3(0, 1, 0), 35.0, 1.0, 0.0, 1.0)   # shortest:111,135
@@ -75,6 +76,7 @@ def _base_config(width, height, seed, kernel, count_work):
     c.sky, c.sky_scale = N.SKY_BLACK, 1.0
     c.min_dis, c.pixel_radius, c.quality_per_sample, c.black_background = 0.0, 0.0, 0.8, 0
     c.nearest_seed, c.normal_mode, c.samples_per_pixel = 0, 0, 1
+    c.adaptive_sampling, c.noise_threshold = 0, 1e-4      # src/config.py:14,17
     c.box_round = 0.0
     c.light_quality = 128.0
     c.f0_variant = 0

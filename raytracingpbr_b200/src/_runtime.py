@@ -55,6 +55,7 @@ def tracer() -> PathTracer:
         cfg.black_background = int(config.BLACK_BACKGROUND)
         cfg.visibility_min, cfg.visibility_max = config.VISIBILITY
         cfg.samples_per_pixel = config.SAMPLES_PER_PIXEL
+        cfg.adaptive_sampling, cfg.noise_threshold = int(config.ADAPTIVE_SAMPLING), config.NOISE_THRESHOLD
         _pt = PathTracer(cfg, scene.OBJECTS, _camera(cam), tm, device=config.DEVICE)
         _dirty_camera = _dirty_scene = False
         _dirty_env = _env is not None

@@ -6,9 +6,10 @@ SAMPLES_PER_PIXEL = 1  # number of samples in one draw call
 QUALITY_PER_SAMPLE = 0.8  # for russian roulette
 
 BLACK_BACKGROUND = False
-ADAPTIVE_SAMPLING = False   # not implemented in the CUDA path
+ADAPTIVE_SAMPLING = False
 
 VISIBILITY = (1e-4, 1e4)
+NOISE_THRESHOLD = 1e-4  # for self-adaptive sampling
 
 MAX_RAYMARCH = 512
 MAX_RAYTRACE = 512

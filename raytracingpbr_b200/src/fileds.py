@@ -23,3 +23,5 @@ ray_buffer = _FieldView(N.BUF_RAY_BUFFER)       # src/fileds.py:7
 image_buffer = _FieldView(N.BUF_IMAGE_BUFFER)   # :8
 image_pixels = _FieldView(N.BUF_IMAGE_PIXELS)   # :9
 u_frame = _runtime.ScalarField(0, camera=False)  # :15
+diff_buffer = _FieldView(N.BUF_DIFF_BUFFER)     # :21 (ADAPTIVE_SAMPLING only)
+diff_pixels = _FieldView(N.BUF_DIFF_PIXELS)     # :22

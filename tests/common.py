@@ -70,7 +70,8 @@ def hostcheck() -> C.CDLL:
     L.hostcheck_pathtrace_ex.restype = C.c_int
     f32p = C.POINTER(C.c_float)
     L.hostcheck_pathtrace_ex.argtypes = [C.POINTER(N.RtpbrConfig), C.POINTER(N.RtpbrCamera), C.POINTER(N.RtpbrObject), C.c_int,
-                                         f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int]
+                                         f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                         f32p]
     L.hostcheck_sd_bunny.restype = C.c_float
     L.hostcheck_sd_bunny.argtypes = [f32p]
     L.hostcheck_sincos.restype = None
@@ -86,7 +87,7 @@ def hostcheck() -> C.CDLL:
 
 
 def hostcheck_pathtrace(cfg, camera, objects, spp, sample_base=0, image=None, rank=0, nranks=1, band=32,
-                        ray_buffer=None, env=None, frame=0):
+                        ray_buffer=None, env=None, frame=0, diff_pixels=None):
     L = hostcheck()
     nobjs = [o.to_native() if isinstance(o, SDFObject) else o for o in objects]
     arr = (N.RtpbrObject * len(nobjs))(*nobjs)
@@ -98,7 +99,8 @@ def hostcheck_pathtrace(cfg, camera, objects, spp, sample_base=0, image=None, ra
                                   ray_buffer.ctypes.data_as(f32p) if ray_buffer is not None else None,
                                   env.ctypes.data_as(f32p) if env is not None else None,
                                   env.shape[0] if env is not None else 0, env.shape[1] if env is not None else 0,
-                                  frame, spp, sample_base, rank, nranks, band)
+                                  frame, spp, sample_base, rank, nranks, band,
+                                  diff_pixels.ctypes.data_as(f32p) if diff_pixels is not None else None)
     assert rc == 0, rc
     return image
 
@@ -140,9 +142,11 @@ def golden_case(name: str):
     elif name == "bunny_glass":
         cfg, objs, cam, tm = scenes.bunny_glass(W, H, max_bounces=int(g["bounces"]), seed=seed, frame=int(g["frame"]))
         env = env_table(g["env_u8"], 1.8, 2.2)                      # bunny_sdf_glass.py:279-280, applied per texel
-    elif name == "src_scene":
+    elif name in ("src_scene", "src_adaptive"):
         cfg, objs, cam, tm = scenes.src_scene(W, H, seed=seed)
         env = env_table(g["env_u8"], 1.4, 2.2)                      # src/ibl.py:33
+        if name == "src_adaptive":
+            cfg.adaptive_sampling, cfg.noise_threshold = 1, float(g["noise_threshold"])
     else:
         raise KeyError(name)
     if "lookfrom" in g:

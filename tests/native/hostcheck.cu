@@ -22,6 +22,7 @@ static void run(const KParams& P, float4* buf)
         int i, j;
         if (!work_to_pixel(P, (uint32_t)w, i, j)) continue;
         const uint32_t pixel = (uint32_t)(i * P.height + j);
+        if (VAR::FAMILY == FAMILY_C && P.adaptive && !(P.diff_pixels[pixel] > P.noise_threshold)) continue;
         float4 acc = buf[pixel];
         if (VAR::FAMILY == FAMILY_C) {
             trace_pixel_c<VAR>(P, pixel, i, j, acc, nullptr);
@@ -37,7 +38,7 @@ static void run(const KParams& P, float4* buf)
 
 HC_API int hostcheck_pathtrace_ex(const RtpbrConfig* cfg, const RtpbrCamera* cam, const RtpbrObject* objs, int n,
                                   float* image_buffer, float* ray_buffer, const float* env, int env_w, int env_h, int frame,
-                                  int spp, uint32_t sample_base, int rank, int nranks, int band)
+                                  int spp, uint32_t sample_base, int rank, int nranks, int band, const float* diff_pixels)
 {
     KParams P;
     memset(&P, 0, sizeof(P));
@@ -52,6 +53,8 @@ HC_API int hostcheck_pathtrace_ex(const RtpbrConfig* cfg, const RtpbrCamera* cam
     P.sample_base = sample_base;
     P.env = env; P.env_w = env_w; P.env_h = env_h;
     P.ray_buffer = ray_buffer;
+    P.diff_pixels = diff_pixels;
+    if (!diff_pixels) P.adaptive = 0;
     float4* buf = reinterpret_cast<float4*>(image_buffer);
     bool bunny = false;
     for (int k = 0; k < n; ++k) bunny = bunny || objs[k].type == RTPBR_SHAPE_BUNNY;
@@ -67,7 +70,8 @@ HC_API int hostcheck_pathtrace_ex(const RtpbrConfig* cfg, const RtpbrCamera* cam
 HC_API int hostcheck_pathtrace(const RtpbrConfig* cfg, const RtpbrCamera* cam, const RtpbrObject* objs, int n, float* image_buffer,
                                int spp, uint32_t sample_base, int rank, int nranks, int band)
 {
-    return hostcheck_pathtrace_ex(cfg, cam, objs, n, image_buffer, nullptr, nullptr, 0, 0, 0, spp, sample_base, rank, nranks, band);
+    return hostcheck_pathtrace_ex(cfg, cam, objs, n, image_buffer, nullptr, nullptr, 0, 0, 0, spp, sample_base, rank, nranks, band,
+                                  nullptr);
 }
 
 HC_API void hostcheck_sincos(float x, float* s, float* c) { sincos_rt(x, *s, *c); }

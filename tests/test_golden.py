@@ -173,6 +173,70 @@ def test_product_bunny_sdf_matches_reference_source():
         assert np.float32(H.hostcheck_sd_bunny(f32p(p))) == want
 
 
+def _adaptive_run(pathtrace_fn, g, cfg):
+    """refresh(); then launches x (pathtrace(); post_process()) like src/renderer.py:25-32, with the oracle's
+    restatement of post_process(); `pathtrace_fn(L, image, ray_buffer, diff_pixels)` renders one launch."""
+    W, H = cfg.width, cfg.height
+    img = np.zeros((W, H, 4), np.float32)
+    rb = np.zeros((W, H, 10), np.float32)
+    pix = np.zeros((W, H, 3), np.float32)
+    dbuf = np.ones((W, H, 2), np.float32)                     # refresh(): diff_buffer = vec2(1), diff_pixels = 1e32
+    dpix = np.full((W, H), 1e32, np.float32)
+    sampled = []
+    for L in range(int(g["launches"])):
+        sampled.append(int((dpix > np.float32(g["noise_threshold"])).sum()))
+        pathtrace_fn(L, img, rb, dpix)
+        po.post_process_src(img, pix, dbuf, dpix, 1.0, 2.2, True)
+    return img, rb, pix, dbuf, dpix, sampled
+
+
+def _check_adaptive(g, img, rb, pix, dbuf, dpix, sampled):
+    assert sampled == g["sampled_per_launch"].tolist() and min(sampled) == 0 and max(sampled) > 0
+    assert np.array_equal(img, g["image_buffer"])
+    assert np.array_equal(rb.view(np.int32), g["ray_buffer"].view(np.int32))
+    assert np.array_equal(dbuf, g["diff_buffer"]) and np.array_equal(dpix, g["diff_pixels"])
+    assert np.array_equal(pix, g["image_pixels"])
+
+
+def test_oracle_adaptive_sampling_matches_reference_source():
+    # src/ with ADAPTIVE_SAMPLING = True: pathtrace() skips converged pixels (src/pathtracer.py:97-101),
+    # post_process() maintains diff_buffer / diff_pixels (src/postprocessor.py:40-43)
+    g, oc, oo, env = oracle_of("src_adaptive")
+    run = lambda L, img, rb, dpix: po.pathtrace_adaptive(oc, oo, 1, img, rb, dpix, env, sample_base=L)
+    _check_adaptive(g, *_adaptive_run(run, g, oc))
+
+
+def test_product_host_code_adaptive_sampling_matches_reference_source():
+    g, cfg, objs, cam, tm, env = common.golden_case("src_adaptive")
+    run = lambda L, img, rb, dpix: common.hostcheck_pathtrace(cfg, cam, objs, 1, sample_base=L, image=img, ray_buffer=rb,
+                                                              env=env, diff_pixels=dpix)
+    _check_adaptive(g, *_adaptive_run(run, g, cfg))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_cuda_adaptive_sampling_matches_reference_source(kernel):
+    from raytracingpbr_b200 import PathTracer, _native as N
+    g, cfg, objs, cam, tm, env = common.golden_case("src_adaptive")
+    cfg.kernel = kernel
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.set_envmap(env)
+        pt.pathtrace(1)                                   # before refresh(): diff_pixels = 0, nothing is sampled
+        assert pt.image_buffer.to_numpy()[..., 3].sum() == 0
+        pt.ctx.set_sample_base(0)
+        pt.refresh()
+        for _ in range(int(g["launches"])):
+            pt.render(1)                                  # pathtrace(); post_process()
+        img, rb = pt.image_buffer.to_numpy(), pt.ray_buffer.to_numpy()
+        dbuf = pt.ctx.download(N.BUF_DIFF_BUFFER)
+        dpix = pt.ctx.download(N.BUF_DIFF_PIXELS)[..., 0]
+        pix = pt.image_pixels.to_numpy()
+    assert np.array_equal(img, g["image_buffer"])
+    assert np.array_equal(rb.view(np.int32), g["ray_buffer"].view(np.int32))
+    assert np.array_equal(dbuf, g["diff_buffer"]) and np.array_equal(dpix, g["diff_pixels"])
+    assert np.array_equal(pix, g["image_pixels"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", SHORTEST, ids=os.path.basename)
 def test_cuda_image_buffer_matches_reference_source(path):

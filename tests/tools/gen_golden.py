@@ -357,7 +357,7 @@ class _SrcFinder:
         exec(compile(src, path, "exec", dont_inherit=True), module.__dict__)
 
 
-def gen_src(name, width, height, launches, seed, spp_per_launch=1):
+def gen_src(name, width, height, launches, seed, spp_per_launch=1, adaptive=False, noise_threshold=None):
     """src/ package (family C): kernel pathtrace() x launches, ray_buffer state persisted between launches."""
     env_u8 = synthetic_env(seed=9)
     ti.tools.imread = lambda path: env_u8
@@ -365,6 +365,9 @@ def gen_src(name, width, height, launches, seed, spp_per_launch=1):
         del sys.modules[k]
     subs = {"src.config": [("image_resolution = (1920 * 4 // 10, 1080 * 4 // 10)", f"image_resolution = ({width}, {height})"),
                            ("SAMPLES_PER_PIXEL = 1  #", f"SAMPLES_PER_PIXEL = {spp_per_launch}  #")]}
+    if adaptive:
+        subs["src.config"] += [("ADAPTIVE_SAMPLING = False", "ADAPTIVE_SAMPLING = True"),
+                               ("NOISE_THRESHOLD = 1e-4", f"NOISE_THRESHOLD = {noise_threshold}")]
     finder = _SrcFinder(subs)
     sys.meta_path.insert(0, finder)
     try:
@@ -403,11 +406,22 @@ def gen_src(name, width, height, launches, seed, spp_per_launch=1):
     t0 = time.time()
     rend.refresh()
     snaps = {}
+    sampled = []
     for L in range(launches):
         ti.rng.launch = L
+        if adaptive:                                   # src/renderer.py:29-32: pathtrace(); post_process()
+            sampled.append(int((fld.diff_pixels.to_numpy() > noise_threshold).sum()))
         pt.pathtrace()
+        if adaptive:
+            import src.postprocessor as pp
+            pp.post_process()
         if L in (0, launches // 2):
             snaps[L] = fld.image_buffer.to_numpy()
+    if adaptive:
+        out["sampled_per_launch"] = np.array(sampled, np.int32)
+        out["noise_threshold"] = np.float32(noise_threshold)
+        out["diff_pixels"] = fld.diff_pixels.to_numpy()
+        out["diff_buffer"] = fld.diff_buffer.to_numpy()
     out["image_buffer"] = fld.image_buffer.to_numpy()
     out["image_buffer_first"] = snaps[0]
     rb = np.zeros((width, height, 10), np.float32)
@@ -416,7 +430,8 @@ def gen_src(name, width, height, launches, seed, spp_per_launch=1):
     rb[..., 6:9] = fld.ray_buffer.member("color")
     rb[..., 9] = fld.ray_buffer.member("depth").astype(np.int32).view(np.float32)
     out["ray_buffer"] = rb
-    rend.post_process()
+    if not adaptive:
+        rend.post_process()
     out["image_pixels"] = fld.image_pixels.to_numpy()
     print(f"  {name}: {width}x{height} x {launches} launches in {time.time() - t0:.1f} s")
     return out
@@ -432,6 +447,7 @@ FIXTURES = {
     "scene_demo": (gen_tokyo, dict(width=8, height=6, spp=2, seed=4, script="main")),
     "bunny_glass": (gen_bunny, dict(width=8, height=6, bounces=16, spp=1, seed=5, frame=7)),
     "src_scene": (gen_src, dict(width=10, height=6, launches=12, seed=6)),
+    "src_adaptive": (gen_src, dict(width=8, height=6, launches=14, seed=8, adaptive=True, noise_threshold=0.2)),
 }
 
 
