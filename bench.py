@@ -105,13 +105,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU legs
-def cpu_sample_columns(width: int, bands: int = 16, cols: int = 2):
+CPU_BANDS, CPU_COLS, CPU_SPP = 32, 2, 64      # bounded CPU sample: 64 spread columns x 1024 rows x 64 spp = 4.19 M samples (~15 s)
+
+
+def cpu_sample_columns(width: int, bands: int = CPU_BANDS, cols: int = CPU_COLS):
     """A bounded, spread-out sample of the workload: `bands` groups of `cols` adjacent columns."""
     step = width // bands
     return [(b * step + step // 2, b * step + step // 2 + cols) for b in range(bands)]
 
 
-def run_cpu_oracle(spp: int, hoisted: bool, threads: int = 0, bands: int = 16, cols: int = 2):
+def run_cpu_oracle(spp: int, hoisted: bool, threads: int = 0, bands: int = CPU_BANDS, cols: int = CPU_COLS):
     """Time the oracle on the sample columns of the C1 image.  Returns (Msamples/s, samples, s)."""
     from oracle import pyoracle as po   # checker / CPU baseline only (never the product path)
     threads = threads or cpu_threads()
@@ -141,7 +144,7 @@ def reference_arm(args, rank: int) -> int:
     if rank != 0:
         return 0
     cores = cpu_threads()
-    spp = 8                                        # 16 bands x 2 cols x 1024 rows x 8 spp = 262,144 samples / step
+    spp = CPU_SPP
     for _ in range(args.warmup):
         run_cpu_oracle(1, hoisted=False, bands=4)
     vals, t_total, n_total = [], 0.0, 0
@@ -151,7 +154,8 @@ def reference_arm(args, rank: int) -> int:
         t_total += dt
         n_total += n
     value = n_total / t_total / 1e6
-    sample = f"32 of 1024 columns (16 spread bands x 2) x 1024 rows x {spp} spp = {n_total // args.steps} samples per step"
+    sample = (f"{CPU_BANDS * CPU_COLS} of 1024 columns ({CPU_BANDS} spread bands x {CPU_COLS}) x 1024 rows x {spp} spp = "
+              f"{n_total // args.steps} samples per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -393,10 +397,10 @@ def main() -> int:
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v_aw, n_aw, dt_aw = run_cpu_oracle(8, hoisted=False)
-        v_h, n_h, dt_h = run_cpu_oracle(16, hoisted=True)
+        v_aw, n_aw, dt_aw = run_cpu_oracle(CPU_SPP, hoisted=False)
+        v_h, n_h, dt_h = run_cpu_oracle(CPU_SPP, hoisted=True)
         cpu = {"value": v_aw, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-               "sample": f"32 of 1024 columns (16 spread bands x 2) x 1024 rows x 8 spp = {n_aw} samples, {dt_aw:.1f} s; "
+               "sample": f"{CPU_BANDS * CPU_COLS} of 1024 columns ({CPU_BANDS} spread bands x {CPU_COLS}) x 1024 rows x {CPU_SPP} spp = {n_aw} samples, {dt_aw:.1f} s; "
                          "as-written (rotation matrices recomputed per object per march step like cornell_box_shortest.py:43)",
                "hoisted_value": v_h, "hoisted_sample": f"{n_h} samples, {dt_h:.1f} s (matrices precomputed)"}
 
