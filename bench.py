@@ -321,6 +321,13 @@ def main() -> int:
         clocks = sampler.stop()
     kernel_ms, kernel_launches = ctx.kernel_time()
     launches = ctx.counters()["launches"] - l0
+    per_rank_kernel_ms = [kernel_ms / max(kernel_launches, 1)]
+    if dist is not None:
+        import torch
+        t = torch.tensor([kernel_ms / max(kernel_launches, 1)], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        per_rank_kernel_ms = [float(x.item()) for x in out]
     ms = max_over_ranks(ms)
     kernel_ms_max = max_over_ranks(kernel_ms)
     total_samples = float(W) * H * spp     # whole job, all ranks (each rank: W*H*SPP)
@@ -369,7 +376,7 @@ def main() -> int:
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": NCU_TRAFFIC_BYTES_C1 if (kernel == N.KERNEL_PERSISTENT and world == 1) else None,
             "algorithmic_bytes_per_launch": alg_bytes,
-            "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "kernel_share_of_step": kernel_ms_max / ms,
+            "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "kernel_ms_per_launch_by_rank": per_rank_kernel_ms, "kernel_share_of_step": kernel_ms_max / ms,
             "note": "this path is instruction-issue bound, not HBM bound (16 B written per sample); see fp32"}
 
     # counted work (untimed extra pass with the counting variant of the kernel)
