@@ -1,6 +1,6 @@
 """src/camera.py -- camera state.  `get_ray` runs inside the CUDA kernel (rt_integrator.cuh
-camera_ray); the GUI easing of SmoothCamera (src/camera.py:82-112) is out of scope: update()
-jumps straight to the target."""
+camera_ray); the easing of SmoothCamera (src/camera.py:82-112)
+is restated on the host."""
 import numpy as np
 
 from . import config
@@ -8,23 +8,42 @@ from ._runtime import ScalarField
 
 
 class SmoothCamera:
+    """src/camera.py:39-112.  The easing kernel `_update` (:82-112) is a few scalar operations per frame, so it
+    runs on the host in fp32; `_rotate` needs the GGUI camera helpers and is out of scope."""
+
     def __init__(self):
         self.position = ScalarField(np.array([0.0, -0.2, 4.0], dtype=np.float32))   # src/main.py:17
         self.lookat = ScalarField(np.array([0.0, -0.2, 3.0], dtype=np.float32))
         self.up = ScalarField(np.array([0.0, 1.0, 0.0], dtype=np.float32))
+        self.position_velocity = ScalarField(np.float32(10), camera=False)           # :53-55
+        self.lookat_velocity = ScalarField(np.float32(10), camera=False)
+        self.up_velocity = ScalarField(np.float32(10), camera=False)
         self.moving = ScalarField(0, camera=False)
 
     def init(self, camera):
-        """camera: anything with curr_position / curr_lookat / curr_up (ti.ui.Camera surface)."""
+        """camera: anything with curr_position / curr_lookat / curr_up (ti.ui.Camera surface); :58-61."""
         self.position[None] = np.asarray(camera.curr_position, dtype=np.float32)
         self.lookat[None] = np.asarray(camera.curr_lookat, dtype=np.float32)
         self.up[None] = np.asarray(camera.curr_up, dtype=np.float32)
 
     def update(self, dt, camera, direction=None):
-        before = (self.position[None].copy(), self.lookat[None].copy(), self.up[None].copy())
-        self.init(camera)
-        after = (self.position[None], self.lookat[None], self.up[None])
-        self.moving[None] = int(any(np.abs(a - b).max() > 1e-3 for a, b in zip(after, before)))
+        """:63-66 without _rotate (GUI)."""
+        self._update(dt, camera.curr_position, camera.curr_lookat, camera.curr_up)
+
+    def _update(self, dt, curr_position, curr_lookat, curr_up):
+        """:82-112: exponential easing towards the GUI camera; sets `moving`, bumps u_frame."""
+        from .fileds import u_frame
+        f = np.float32
+        dt = f(dt)
+        diffs = []
+        for fld, vel, cur in ((self.position, self.position_velocity, curr_position),
+                              (self.lookat, self.lookat_velocity, curr_lookat), (self.up, self.up_velocity, curr_up)):
+            val = fld[None]
+            diff = np.asarray(cur, dtype=np.float32) - val
+            fld[None] = (val + diff * np.clip(vel[None] * dt, f(0), f(1))).astype(np.float32)
+            diffs.append(float(np.abs(diff).max()))
+        self.moving[None] = int(max(diffs) > 1e-3)
+        u_frame[None] = u_frame[None] + 1
 
 
 smooth = SmoothCamera()

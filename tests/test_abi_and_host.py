@@ -118,3 +118,36 @@ def test_product_shard_mapping_on_host():
         assert (part[~own] == 0).all() and (part[own][..., 3] == 2).all()
         acc += part
     assert np.array_equal(acc, full)
+
+
+def test_src_shaped_surface_imports_without_side_effects():
+    # module layout of the reference's src/ package; importing creates no GPU context (lazy runtime)
+    from raytracingpbr_b200.src import _runtime, camera, config, fileds, pathtracer, postprocessor, renderer, scene, sdf
+    assert _runtime._pt is None
+    assert sdf.SHAPE.SPHERE == 1 and sdf.SHAPE.PLANE == 5                       # src/sdf.py:12-18
+    assert len(scene.OBJECTS) == 7 and [o.type for o in scene.OBJECTS] == sorted(o.type for o in scene.OBJECTS)   # src/scene.py:33
+    assert fileds.image_buffer.shape == tuple(config.image_resolution) == (768, 432)
+    assert camera.camera_vfov[None] == 35.0 and camera.camera_aperture[None] == 0.01 and camera.camera_focus[None] == 4.0
+    for fn in (renderer.render, renderer.refresh, pathtracer.pathtrace, postprocessor.post_process, scene.build_scene):
+        assert callable(fn)
+
+
+def test_smooth_camera_easing_follows_reference_update():
+    # src/camera.py:82-112: position += (target - position) * clamp(velocity * dt, 0, 1); moving flag; u_frame += 1
+    from raytracingpbr_b200.src import camera, fileds
+
+    class Cam:
+        curr_position = np.array([1, -0.2, 4], np.float32)
+        curr_lookat = np.array([0, -0.2, 3], np.float32)
+        curr_up = np.array([0, 1, 0], np.float32)
+    s = camera.SmoothCamera()
+    f0 = fileds.u_frame[None]
+    s.update(0.05, Cam)
+    np.testing.assert_allclose(s.position[None], [0.5, -0.2, 4.0], atol=1e-6)
+    assert s.moving[None] == 1 and fileds.u_frame[None] == f0 + 1
+    for _ in range(60):
+        s.update(0.05, Cam)
+    np.testing.assert_allclose(s.position[None], [1, -0.2, 4], atol=1e-5)
+    assert s.moving[None] == 0
+    s.update(0.5, Cam)                                # velocity * dt > 1 clamps to 1
+    np.testing.assert_allclose(s.position[None], [1, -0.2, 4], atol=1e-6)
