@@ -228,3 +228,31 @@ def test_src_progressive_alpha_counts_paths():
     want = po.pathtrace(oc, oo, 64, env=_synthetic_env(seed=6), ray_buffer=orb, i0=100, i1=102)
     assert np.array_equal(buf[100:102], want[100:102])
     assert np.array_equal(rb[100:102].view(np.int32), orb[100:102].view(np.int32))
+
+
+def test_src_shaped_modules_drive_the_same_kernels():
+    # raytracingpbr_b200.src.* (the reference's src/ layout) vs PathTracer driven directly
+    from raytracingpbr_b200.src import _runtime, camera, config, fileds, renderer, scene
+    _runtime.close()
+    config.image_resolution = (64, 36)
+    config.SEED = 3
+    config.SAMPLES_PER_FRAME = 2
+    cfg, objs, cam, tm = scenes.src_scene(64, 36, seed=3)
+    camera.aspect_ratio[None] = cam.aspect
+    env = _synthetic_env(seed=8)
+    _runtime.set_env(env)
+    scene.build_scene()                       # src/main.py:21
+    renderer.render(True)                     # refresh(); pathtrace() x SAMPLES_PER_FRAME; post_process()
+    renderer.render(False)
+    got = fileds.image_buffer.to_numpy()
+    pix = fileds.image_pixels.to_numpy()
+    _runtime.close()
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.set_envmap(env)
+        pt.refresh()
+        pt.pathtrace(2)
+        pt.pathtrace(2)
+        pt.post_process()
+        assert np.array_equal(got, pt.image_buffer.to_numpy())
+        assert np.array_equal(pix, pt.image_pixels.to_numpy())
+    assert got[..., 3].sum() > 0 and pix.max() <= 1.0
