@@ -172,23 +172,21 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                 int pi = (int)(pixel / (uint32_t)P.height), pj = (int)(pixel - (uint32_t)pi * (uint32_t)P.height);
 
                 // ---- run the slot's state machine until it needs marching again (or dies)
-                if (VAR::FAMILY == FAMILY_C) {
-                    if (st == ST_HIT || st == ST_MISS) {
+                for (;;) {
+                    if (VAR::FAMILY != FAMILY_C) {
+                        if (st == ST_HIT) {
+                            if (VAR::COUNT) { cnt.normals++; cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                            st = (on_hit<VAR>(P, p) && begin_bounce<VAR>(P, p)) ? ST_READY : ST_DONE;
+                        } else if (st == ST_MISS) {
+                            if (VAR::COUNT) { cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                            on_miss<VAR>(P, p);
+                            st = ST_DONE;
+                        }
+                    } else if (st == ST_HIT || st == ST_MISS) {
                         c_after_march<VAR>(P, p, st == ST_HIT ? MARCH_HIT : MARCH_MISS, VAR::COUNT ? &cnt : nullptr);
                         k++;
                         st = ST_ADVANCE;
                     }
-                } else {
-                    if (st == ST_HIT) {
-                        if (VAR::COUNT) { cnt.normals++; cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
-                        st = (on_hit<VAR>(P, p) && begin_bounce<VAR>(P, p)) ? ST_READY : ST_DONE;
-                    } else if (st == ST_MISS) {
-                        if (VAR::COUNT) { cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
-                        on_miss<VAR>(P, p);
-                        st = ST_DONE;
-                    }
-                }
-                for (;;) {
                     if (VAR::FAMILY == FAMILY_C) {
                         if (st == ST_ADVANCE) {
                             TaskC task; task.launch = samp; task.k = k;
@@ -252,7 +250,14 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                         begin_path<VAR>(P, pixel, pi, pj, P.sample_base + (uint32_t)samp, p);
                         st = begin_bounce<VAR>(P, p) ? ST_READY : ST_DONE;
                     }
+#if defined(RT_JIT_SCENE)
+                    // irregular rays (non-finite origin / direction) never enter the specialised march loop
+                    if (st == ST_READY && ray_is_irregular(p.m))
+                        st = march_to_end_generic<VAR>(P, p.m) == MARCH_HIT ? ST_HIT : ST_MISS;
+                    const bool more = st == ST_HIT || st == ST_MISS || (VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE));
+#else
                     const bool more = VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE);
+#endif
                     if (__ballot_sync(kFull, more) == 0u) break;
                 }
 
