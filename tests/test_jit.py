@@ -125,3 +125,16 @@ def test_jit_and_aot_kernels_give_the_same_bits(name):
                 pytest.skip("NVRTC not available on this machine: " + msg)
             assert active == jit, msg
     assert np.array_equal(out[True], out[False])
+
+
+@pytest.mark.gpu
+def test_device_bit_identity_along_real_rays(tmp_path):
+    """Every scene evaluation of 512 x 512 x 16 spp Cornell paths: generic nearest() vs the generated
+    jit_nearest() / jit_nearest_dist() ON THE DEVICE (ranged sqrt, packed f32x2 pairs, doubled distances)."""
+    import sys
+    sys.path.insert(0, os.path.join(common.ROOT, "tools"))
+    import jit_device_check
+    exe = jit_device_check.build(size=512, spp=16, out_dir=str(tmp_path))
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert " 0 mismatches" in out.stdout
