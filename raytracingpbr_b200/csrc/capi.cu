@@ -103,6 +103,7 @@ struct RtpbrContext {
     bool jit_enabled = true, jit_stale = true;
     std::unique_ptr<rt::jit::Kernel> jit_kernel;
     int jit_blocks_per_sm = 0;
+    int jit_block = rt::kPoolBlock, jit_slots = rt::kPoolSlots, jit_min_blocks = rt::kPoolMinBlocks;   // pool geometry of the NVRTC build
     std::string jit_log = "not built yet";
     void* nccl_comm = nullptr;
     int nccl_rank = 0, nccl_nranks = 1;
@@ -183,6 +184,9 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     rt::fill_shard(c->P, 0, 1, 32);
     rt::fill_frame(c->P, 0);
     if (const char* j = getenv("RTPBR_JIT")) c->jit_enabled = atoi(j) != 0;
+    if (const char* v = getenv("RTPBR_POOL_SLOTS")) { int x = atoi(v); if (x >= 32 && x <= 128 && x % 4 == 0) c->jit_slots = x; }
+    if (const char* v = getenv("RTPBR_POOL_BLOCK")) { int x = atoi(v); if (x >= 32 && x <= 1024 && x % 32 == 0) c->jit_block = x; }
+    if (const char* v = getenv("RTPBR_POOL_MIN_BLOCKS")) { int x = atoi(v); if (x >= 1 && x <= 16) c->jit_min_blocks = x; }
     c->P.resolve_min = 8;
     if (const char* q = getenv("RTPBR_RESOLVE_MIN")) {
         int v = atoi(q);
@@ -358,7 +362,10 @@ static void ensure_jit(RtpbrContext* c)
     const rt::jit::Source src = rt::jit::generate(c->cfg, c->scene.data(), (int)c->scene.size());
     std::shared_ptr<std::vector<char>> cubin;
     std::string log;
-    if (!rt::jit::compile(src.text, rt::jit::default_include_dir(), cubin, log)) {
+    const size_t smem = rt::pool_smem_bytes_for(c->jit_block, c->jit_slots);
+    const std::vector<std::string> defs = { "-DRT_POOL_BLOCK=" + std::to_string(c->jit_block), "-DRT_POOL_SLOTS=" + std::to_string(c->jit_slots),
+                                            "-DRT_POOL_MIN_BLOCKS=" + std::to_string(c->jit_min_blocks) };
+    if (!rt::jit::compile(src.text, rt::jit::default_include_dir(), cubin, log, defs)) {
         c->jit_enabled = false;
         c->jit_log = "NVRTC failed, using the ahead-of-time kernel: " + log;
         fprintf(stderr, "librtpbr: %s\n", c->jit_log.c_str());
@@ -366,15 +373,16 @@ static void ensure_jit(RtpbrContext* c)
     }
     std::unique_ptr<rt::jit::Kernel> k(new rt::jit::Kernel());
     std::string err;
-    if (!rt::jit::load(*cubin, src.kernel_name.c_str(), rt::pool_dynamic_smem(), *k, err) ||
-        !rt::jit::occupancy(*k, rt::kPoolBlock, rt::pool_dynamic_smem(), &c->jit_blocks_per_sm, err) || c->jit_blocks_per_sm < 1) {
+    if (!rt::jit::load(*cubin, src.kernel_name.c_str(), smem, *k, err) ||
+        !rt::jit::occupancy(*k, c->jit_block, smem, &c->jit_blocks_per_sm, err) || c->jit_blocks_per_sm < 1) {
         c->jit_enabled = false;
         c->jit_log = "loading the specialised kernel failed, using the ahead-of-time kernel: " + err;
         fprintf(stderr, "librtpbr: %s\n", c->jit_log.c_str());
         return;
     }
     c->jit_log = "scene-specialised kernel active (" + std::to_string(k->registers) + " registers, " +
-                 std::to_string(c->jit_blocks_per_sm) + " CTAs/SM)";
+                 std::to_string(c->jit_blocks_per_sm) + " CTAs/SM x " + std::to_string(c->jit_block) + " threads, " +
+                 std::to_string(c->jit_slots) + " slots/warp)";
     c->jit_kernel = std::move(k);
 }
 
@@ -384,13 +392,14 @@ static int launch_pool_chunk(RtpbrContext* c, const rt::KernelSelect& sel, std::
     ensure_jit(c);
     if (c->jit_kernel) {
         long long grid = (long long)c->sm_count * c->jit_blocks_per_sm;
-        const long long per_cta = (long long)(rt::kPoolBlock / 32) * rt::kPoolSlots;
+        const long long per_cta = (long long)(c->jit_block / 32) * c->jit_slots;
         const long long need = (long long)((items + per_cta - 1) / per_cta);
         if (grid > need) grid = need;
         CUDA_TRY(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->stream));
         CUDA_TRY(cudaEventRecord(ev.first, c->stream));
         std::string err;
-        if (!rt::jit::launch(*c->jit_kernel, c->P, (int)grid, rt::kPoolBlock, rt::pool_dynamic_smem(), c->stream, err))
+        if (!rt::jit::launch(*c->jit_kernel, c->P, (int)grid, c->jit_block, rt::pool_smem_bytes_for(c->jit_block, c->jit_slots),
+                             c->stream, err))
             return fail(RTPBR_ERR_CUDA, err);
         CUDA_TRY(cudaEventRecord(ev.second, c->stream));
         c->blocks_per_sm = c->jit_blocks_per_sm;

@@ -112,19 +112,22 @@ std::string default_include_dir()
 }
 
 bool compile(const std::string& source, const std::string& include_dir, std::shared_ptr<std::vector<char>>& cubin,
-             std::string& log)
+             std::string& log, const std::vector<std::string>& defines)
 {
     std::lock_guard<std::mutex> lock(g_mu);
-    auto it = g_cache.find(source);
+    std::string key = source;
+    for (const std::string& d : defines) key += "\n//" + d;
+    auto it = g_cache.find(key);
     if (it != g_cache.end()) { cubin = it->second; log = "cached"; return true; }
     if (!load_nvrtc(log)) return false;
     void* prog = nullptr;
     int rc = g_nvrtc.CreateProgram(&prog, source.c_str(), "rtpbr_scene.cu", 0, nullptr, nullptr);
     if (rc != 0) { log = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(rc); return false; }
     const std::string inc = "-I" + include_dir;
-    const char* opts[] = { "--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "--prec-div=true", "--prec-sqrt=true",
-                           "-lineinfo", inc.c_str() };
-    rc = g_nvrtc.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+    std::vector<const char*> opts = { "--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "--prec-div=true",
+                                      "--prec-sqrt=true", "-lineinfo", inc.c_str() };
+    for (const std::string& d : defines) opts.push_back(d.c_str());
+    rc = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
     size_t n = 0;
     g_nvrtc.GetProgramLogSize(prog, &n);
     std::string plog(n, '\0');
@@ -140,7 +143,7 @@ bool compile(const std::string& source, const std::string& include_dir, std::sha
     if (rc == 0) rc = g_nvrtc.GetCUBIN(prog, out->data());
     g_nvrtc.DestroyProgram(&prog);
     if (rc != 0 || sz == 0) { log = "nvrtcGetCUBIN failed"; return false; }
-    g_cache[source] = out;
+    g_cache[key] = out;
     cubin = out;
     log = plog;
     return true;

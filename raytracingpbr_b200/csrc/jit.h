@@ -22,7 +22,7 @@ struct Kernel {
 // Compile `source` to an sm_100a CUBIN with NVRTC (works without a GPU).  `include_dir` must
 // contain pool_kernel.cuh and friends.  Results are cached in-process by source text.
 bool compile(const std::string& source, const std::string& include_dir, std::shared_ptr<std::vector<char>>& cubin,
-             std::string& log);
+             std::string& log, const std::vector<std::string>& defines = {});
 // Load a CUBIN into the current (primary) context and look the kernel up.
 bool load(const std::vector<char>& cubin, const char* kernel_name, size_t dynamic_smem, Kernel& out, std::string& err);
 bool occupancy(const Kernel& k, int block, size_t dynamic_smem, int* blocks_per_sm, std::string& err);

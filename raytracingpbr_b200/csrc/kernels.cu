@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_refresh_adaptive(float2* diff_buffer, f
 // Host-side launchers (called from capi.cu)
 // ------------------------------------------------------------------------------------------
 template <int NSLOT>
-constexpr size_t pool_smem_bytes() { return (size_t)(kPoolBlock / 32) * (F_COUNT * NSLOT + 2 * (NSLOT / 4)) * sizeof(uint32_t); }
+constexpr size_t pool_smem_bytes() { return (size_t)pool_smem_bytes_for(kPoolBlock, NSLOT); }
 
 template <class VAR>
 static cudaError_t launch_pool_t(const KParams& P, int grid, cudaStream_t stream)

@@ -41,6 +41,7 @@ enum : int { ST_NONE = 0, ST_READY = 1, ST_HIT = 2, ST_MISS = 3, ST_DONE = 4, ST
 enum : int { F_ROX = 0, F_ROY, F_ROZ, F_RDX, F_RDY, F_RDZ, F_COLX, F_COLY, F_COLZ, F_T, F_W, F_S, F_D, F_TEVAL,
              F_STEPS, F_IDX, F_DEPTH, F_RNGN, F_PIXEL, F_SAMP, F_K, F_STATUS, F_ACCX, F_ACCY, F_ACCZ, F_ACCW,
              F_COUNT };
+static_assert(F_COUNT == kPoolSlotWords, "kernels_config.h: kPoolSlotWords");
 
 template <int NSLOT>
 struct Pool {
