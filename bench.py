@@ -236,11 +236,17 @@ def main() -> int:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel", default="persistent", choices=["persistent", "simple"])
     ap.add_argument("--counters", action="store_true", help="extra untimed pass with work counters (default at N=1)")
-    ap.add_argument("--workload", default="c1", choices=list(EXTRA_WORKLOADS) + ["c1"],
-                    help="c1 = the headline (default); c2 / c3 = BASELINE.json configs[2] / configs[3], informational")
+    ap.add_argument("--workload", default="c1", choices=list(EXTRA_WORKLOADS) + ["c1", "c4"],
+                    help="c1 = the headline (default); c2 / c3 = BASELINE.json configs[2] / configs[3], informational; "
+                         "c4 = configs[4]: 4096 x 4096 x 1024 spp tile-sharded over the ranks (strong scaling, run under torchrun)")
     args = ap.parse_args()
-    if args.workload != "c1":
+    if args.workload in EXTRA_WORKLOADS:
         return extra_workload(args)
+    global W, H, SPP, WORKLOAD
+    strong = args.workload == "c4"
+    if strong:
+        W, H, SPP = 4096, 4096, 1024
+        WORKLOAD = "C4: cornell_box_shortest scene, 4096x4096, 1024 spp, max 8 bounces, tile-sharded"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -279,7 +285,8 @@ def main() -> int:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    spp = SPP * world          # weak scaling: per-GPU samples fixed (W*H*SPP), tiles sharded by column band
+    # weak scaling (c1): per-GPU samples fixed (W*H*SPP), tiles sharded by column band; c4: the job is fixed
+    spp = SPP if strong else SPP * world
     kernel = N.KERNEL_PERSISTENT if args.kernel == "persistent" else N.KERNEL_SIMPLE
     cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=BOUNCES, seed=0, kernel=kernel)
     pt = PathTracer(cfg, objs, cam, tm, device=local_rank)
@@ -335,7 +342,8 @@ def main() -> int:
     value = total_samples / (ms_per_step * 1e-3) / 1e6
 
     # ---- leg 2: end to end through the public API with host buffers --------------------
-    host_img = np.empty((W, H, 4), dtype=np.float32)
+    pinned = N.PinnedArray((W, H, 4), np.float32)          # page-locked destination of the per-step device -> host read
+    host_img = pinned.array
     h2d = sum(len(bytes(o.to_native())) for o in objs) + len(bytes(cam.to_native()))
     d2h = host_img.nbytes if rank == 0 else 0
 
@@ -363,6 +371,8 @@ def main() -> int:
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_samples * args.steps / e2e_s / 1e6
     checksum = float(host_img[..., 3].sum()) if rank == 0 else 0.0
+    host_img = None
+    pinned.free()
 
     # ---- roofline of the dominant kernel ---------------------------------------------
     info = ctx.device_info()
@@ -371,17 +381,18 @@ def main() -> int:
     local_pixels = W * H / world
     alg_bytes = (BYTES_PER_SAMPLE * local_pixels * spp if kernel == N.KERNEL_PERSISTENT
                  else BYTES_PER_PIXEL_PER_LAUNCH * local_pixels)
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    launches_per_step = max(kernel_launches, 1) / args.steps      # > 1 when the spp are chunked to the scratch budget
+    achieved = alg_bytes / (k_ms * launches_per_step * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "k_pathtrace_pool" if kernel == N.KERNEL_PERSISTENT else "k_pathtrace_simple",
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": NCU_TRAFFIC_BYTES_C1 if (kernel == N.KERNEL_PERSISTENT and world == 1) else None,
+            "traffic": NCU_TRAFFIC_BYTES_C1 if (kernel == N.KERNEL_PERSISTENT and world == 1 and not strong) else None,
             "algorithmic_bytes_per_launch": alg_bytes,
             "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "kernel_ms_per_launch_by_rank": per_rank_kernel_ms, "kernel_share_of_step": kernel_ms_max / ms,
             "note": "this path is instruction-issue bound, not HBM bound (16 B written per sample); see fp32"}
 
     # counted work (untimed extra pass with the counting variant of the kernel)
     fp32 = None
-    if rank == 0 and (args.counters or world == 1):
+    if rank == 0 and (args.counters or world == 1) and not strong:
         ccfg, _, _, _ = scenes.cornell_box_shortest(W, H, max_bounces=BOUNCES, seed=0, kernel=kernel, count_work=True)
         with PathTracer(ccfg, objs, cam, tm, device=local_rank) as cpt:
             cpt.refresh()
@@ -403,7 +414,7 @@ def main() -> int:
 
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not strong:
         v_aw, n_aw, dt_aw = run_cpu_oracle(CPU_SPP, hoisted=False)
         v_h, n_h, dt_h = run_cpu_oracle(CPU_SPP, hoisted=True)
         cpu = {"value": v_aw, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
@@ -414,10 +425,11 @@ def main() -> int:
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "spp_per_step": spp, "max_bounces": BOUNCES,
-                       "sharding": f"{world} ranks, {BAND}-column interleaved bands, spp x {world}" if world > 1 else "none",
+                       "sharding": (f"{world} ranks, {BAND}-column interleaved bands" + ("" if strong else f", spp x {world}")) if world > 1 else "none",
                        "l2": "flushed between steps by a 256 MiB memset on the launch stream (inside the timed region)",
                        "kernel": args.kernel, "blocks_per_sm": info["blocks_per_sm"], "jit": ctx.jit_status()[1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

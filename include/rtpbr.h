@@ -176,6 +176,9 @@ RTPBR_API int rtpbr_download(RtpbrContext* ctx, int which, void* host, size_t by
 /* resume from a saved accumulation buffer (reference has no checkpointing) */
 RTPBR_API int rtpbr_upload(RtpbrContext* ctx, int which, const void* host, size_t bytes);
 RTPBR_API int rtpbr_sync(RtpbrContext* ctx);
+/* page-locked host memory for rtpbr_download / rtpbr_upload / rtpbr_set_envmap buffers (cudaHostAlloc / cudaFreeHost) */
+RTPBR_API int rtpbr_alloc_host(size_t bytes, void** out);
+RTPBR_API int rtpbr_free_host(void* ptr);
 /* benchmark hygiene: evict L2 by writing a 256 MiB scratch buffer on the launch stream */
 RTPBR_API int rtpbr_flush_l2(RtpbrContext* ctx);
 

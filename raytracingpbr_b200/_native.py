@@ -30,7 +30,7 @@ CNT_NAMES = ("scene_evals", "rays", "normals", "samples", "march_iters", "march_
 EXPORTS = (
     "rtpbr_create", "rtpbr_destroy", "rtpbr_set_scene", "rtpbr_set_camera", "rtpbr_set_envmap", "rtpbr_set_frame",
     "rtpbr_set_sample_base", "rtpbr_set_shard", "rtpbr_refresh", "rtpbr_pathtrace", "rtpbr_post_process",
-    "rtpbr_download", "rtpbr_upload", "rtpbr_sync", "rtpbr_flush_l2", "rtpbr_timer_start", "rtpbr_timer_stop", "rtpbr_kernel_time",
+    "rtpbr_download", "rtpbr_upload", "rtpbr_sync", "rtpbr_alloc_host", "rtpbr_free_host", "rtpbr_flush_l2", "rtpbr_timer_start", "rtpbr_timer_stop", "rtpbr_kernel_time",
     "rtpbr_get_counters", "rtpbr_device_info", "rtpbr_nccl_unique_id", "rtpbr_nccl_init", "rtpbr_reduce_tiles",
     "rtpbr_device_ptr", "rtpbr_set_jit", "rtpbr_jit_status", "rtpbr_jit_generate", "rtpbr_jit_compile_check", "rtpbr_last_error", "rtpbr_version", "rtpbr_sizeof_config", "rtpbr_sizeof_object",
     "rtpbr_sizeof_camera",
@@ -119,6 +119,8 @@ def lib() -> C.CDLL:
         "rtpbr_upload": [vp, C.c_int, vp, C.c_size_t],
         "rtpbr_sync": [vp],
         "rtpbr_flush_l2": [vp],
+        "rtpbr_alloc_host": [C.c_size_t, C.POINTER(vp)],
+        "rtpbr_free_host": [vp],
         "rtpbr_timer_start": [vp],
         "rtpbr_timer_stop": [vp, C.POINTER(C.c_float)],
         "rtpbr_kernel_time": [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
@@ -151,6 +153,31 @@ def lib() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise RtpbrError(rc, (lib().rtpbr_last_error() or b"").decode("utf-8", "replace"))
+
+
+class PinnedArray:
+    """Page-locked host array (cudaHostAlloc) exposed as a numpy view; free() or use as a context manager."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self._L = lib()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(self._L.rtpbr_alloc_host(self.nbytes, C.byref(p)))
+        self._p = p
+        buf = (C.c_char * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._L.rtpbr_free_host(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
 
 
 def jit_source(cfg: RtpbrConfig, objects) -> str:

@@ -561,6 +561,20 @@ int rtpbr_sync(RtpbrContext* c)
     return RTPBR_OK;
 }
 
+int rtpbr_alloc_host(size_t bytes, void** out)
+{
+    if (!out || bytes == 0) return fail(RTPBR_ERR_ARG, "bad argument");
+    *out = nullptr;
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return RTPBR_OK;
+}
+
+int rtpbr_free_host(void* ptr)
+{
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return RTPBR_OK;
+}
+
 int rtpbr_flush_l2(RtpbrContext* c)
 {
     if (!c) return fail(RTPBR_ERR_ARG, "null context");

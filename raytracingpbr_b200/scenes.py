@@ -133,6 +133,24 @@ def cornell_box(width: int = 480, height: int = 480, max_bounces: int = 128, see
     return c, objects, camera, tonemap
 
 
+def cornell_box_v2(width: int = 512, height: int = 512, max_bounces: int = 3, seed: int = 0,
+                   kernel: int = N.KERNEL_PERSISTENT, count_work: bool = False):
+    """examples/cornell_box/cornell_box_v2.py (family B): cornell_box.py at x10 world scale with rounded boxes."""
+    c = _base_config(width, height, seed, kernel, count_work)
+    c.family = N.FAMILY_B
+    c.max_bounces = max_bounces                      # MAX_RAYTRACE = 3, cornell_box_v2.py:21
+    c.max_steps = 512                                # :20
+    c.marcher = N.MARCH_PLAIN                        # :187-196
+    c.t_start, c.hit_eps, c.t_far = 0.05, 0.001, 2000.0              # MIN_DIS, PRECISION, MAX_DIS :15-17
+    c.normal_h = 0.001                               # e = vec2(1, -1) * PRECISION :180
+    c.box_round = 0.01                               # :130
+    c.bsdf, c.f0_variant = 1, 0
+    objects = _cornell_pbr_objects(-253, world_scale=10.0)            # :134-136, :156
+    camera = Camera(vec3(0, 0, 35), vec3(0, 0, -10), vec3(0, 1, 0), 35.0, width / height, 0.01, 4.0)   # :27-31, :346
+    tonemap = dict(mode=1, exposure=1.0, gamma=2.2)
+    return c, objects, camera, tonemap
+
+
 def cornell_box_v3(width: int = 512, height: int = 512, max_bounces: int = 3, seed: int = 0,
                    kernel: int = N.KERNEL_PERSISTENT, count_work: bool = False):
     """examples/cornell_box/cornell_box_v3/ (family B): world x10, rounded boxes, enhanced sphere tracing."""

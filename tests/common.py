@@ -132,6 +132,8 @@ def golden_case(name: str):
         cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=int(g["bounces"]), seed=seed)
     elif name == "cornell_box":
         cfg, objs, cam, tm = scenes.cornell_box(W, H, max_bounces=int(g["bounces"]), seed=seed)
+    elif name == "cornell_v2":
+        cfg, objs, cam, tm = scenes.cornell_box_v2(W, H, max_bounces=int(g["bounces"]), seed=seed)
     elif name == "cornell_v3":
         cfg, objs, cam, tm = scenes.cornell_box_v3(W, H, max_bounces=int(g["bounces"]), seed=seed)
     elif name == "tokyo_ibl":

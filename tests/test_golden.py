@@ -82,7 +82,7 @@ def test_product_host_code_matches_reference_source(path):
     assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, S), g["image_buffer"])
 
 
-FAMILY_B = ["cornell_box", "cornell_v3", "tokyo_ibl", "scene_demo", "bunny_glass"]
+FAMILY_B = ["cornell_box", "cornell_v2", "cornell_v3", "tokyo_ibl", "scene_demo", "bunny_glass"]
 
 
 def oracle_of(name):
@@ -122,7 +122,7 @@ def test_oracle_family_bc_functions_match_reference_source(name):
         rec = np.zeros(7, np.float32)
         for row in g["raycast"]:
             L.orc_raycast_g(C.byref(oc), oo, n, f32p(row[0:3]), f32p(row[3:6]), f32p(rec))
-            pos = row[8:11] if name == "cornell_box" else row[7:10]
+            pos = row[8:11] if name in ("cornell_box", "cornell_v2") else row[7:10]
             assert rec[0] == row[6] and np.array_equal(rec[4:7], pos)
     if "bunny_sd" in g:                                        # sd_bunny, bunny_sdf_glass.py:149-203
         for p, want in zip(g["bunny_points"], g["bunny_sd"]):

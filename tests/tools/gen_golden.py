@@ -183,21 +183,29 @@ def random_rays(rnd, n, origin_z, spread, target_box):
     return rays
 
 
-def gen_cornell_box(name, width, height, bounces, spp, seed):
-    """examples/cornell_box/cornell_box.py (family B, plain marcher, PBR materials)."""
-    subs = [("image_resolution = (1920 // 4, 1920 // 4)", f"image_resolution = ({width}, {height})"),
-            ("MAX_RAYTRACE = 128", f"MAX_RAYTRACE = {bounces}")]
-    m = load_script("examples/cornell_box/cornell_box.py", f"ref_cornell_box_{name}", subs)
+def gen_cornell_box(name, width, height, bounces, spp, seed, v2=False):
+    """examples/cornell_box/cornell_box.py (family B, plain marcher, PBR materials) or cornell_box_v2.py."""
+    if v2:
+        subs = [("image_resolution = (512, 512)", f"image_resolution = ({width}, {height})"),
+                ("MAX_RAYTRACE = 3", f"MAX_RAYTRACE = {bounces}")]
+        m = load_script("examples/cornell_box/cornell_box_v2.py", f"ref_cornell_box_{name}", subs)
+    else:
+        subs = [("image_resolution = (1920 // 4, 1920 // 4)", f"image_resolution = ({width}, {height})"),
+                ("MAX_RAYTRACE = 128", f"MAX_RAYTRACE = {bounces}")]
+        m = load_script("examples/cornell_box/cornell_box.py", f"ref_cornell_box_{name}", subs)
     install_rng(seed)
     rnd = np.random.default_rng(77)
+    k = 10.0 if v2 else 1.0
     out = {"width": width, "height": height, "bounces": bounces, "spp": spp, "seed": seed,
-           "lookfrom": np.array([0, 0, 3], np.float32), "lookat": np.array([0, 0, -1], np.float32)}
-    pts = rnd.uniform(-1.1, 1.1, (10, 3)).astype(np.float32)
+           "lookfrom": np.array([0, 0, 35 if v2 else 3], np.float32), "lookat": np.array([0, 0, -10 if v2 else -1], np.float32)}
+    pts = (rnd.uniform(-1.1, 1.1, (10, 3)) * k).astype(np.float32)
     npts = np.array([[0.6, -0.8, 0.6, 2], [-0.8, 0.1, 0.2, 3], [0.1, 0.799, 0.05, 7], [0.3, -0.3, 0.45, 6]], np.float32)
-    probe_functions(m, out, 8, pts, npts, random_rays(rnd, 6, 3.0, 0.5, 0.9),
+    npts[:, :3] *= k
+    probe_functions(m, out, 8, pts, npts, random_rays(rnd, 6, 3.0 * (35 / 3 if v2 else 1), 0.5 * k, 0.9 * k),
                     lambda rec: np.concatenate([[float(rec.hit), rec.distance], vlist(rec.position)]))
     t0 = time.time()
-    run_samples(m, m.render, (vec3(0, 0, 3), vec3(0, 0, -1), vec3(0, 1, 0), False), spp, out)
+    cam_args = (vec3(0, 0, 35), vec3(0, 0, -10), vec3(0, 1, 0), False) if v2 else (vec3(0, 0, 3), vec3(0, 0, -1), vec3(0, 1, 0), False)
+    run_samples(m, m.render, cam_args, spp, out)
     out["image_pixels"] = m.image_pixels.to_numpy()
     print(f"  {name}: {width}x{height}x{spp} spp in {time.time() - t0:.1f} s")
     return out
@@ -442,6 +450,7 @@ FIXTURES = {
     "shortest_3b": (gen_shortest, dict(width=12, height=10, bounces=3, spp=2, seed=0)),      # the file as shipped (3 bounces)
     "shortest_8b": (gen_shortest, dict(width=10, height=8, bounces=8, spp=2, seed=7)),       # BASELINE configs[1] bounce count
     "cornell_box": (gen_cornell_box, dict(width=8, height=8, bounces=6, spp=2, seed=1)),
+    "cornell_v2": (gen_cornell_box, dict(width=8, height=8, bounces=3, spp=2, seed=9, v2=True)),
     "cornell_v3": (gen_cornell_v3, dict(width=8, height=8, bounces=3, spp=2, seed=2)),
     "tokyo_ibl": (gen_tokyo, dict(width=12, height=8, spp=3, seed=3)),
     "scene_demo": (gen_tokyo, dict(width=8, height=6, spp=2, seed=4, script="main")),
