@@ -4,6 +4,7 @@
 
 #include <dlfcn.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -143,6 +144,10 @@ bool compile(const std::string& source, const std::string& include_dir, std::sha
     if (rc == 0) rc = g_nvrtc.GetCUBIN(prog, out->data());
     g_nvrtc.DestroyProgram(&prog);
     if (rc != 0 || sz == 0) { log = "nvrtcGetCUBIN failed"; return false; }
+    if (const char* dump = getenv("RTPBR_JIT_DUMP")) {   // debugging aid: <dump>.cu / <dump>.cubin for nvdisasm
+        if (FILE* f = fopen((std::string(dump) + ".cu").c_str(), "w")) { fwrite(source.data(), 1, source.size(), f); fclose(f); }
+        if (FILE* f = fopen((std::string(dump) + ".cubin").c_str(), "wb")) { fwrite(out->data(), 1, out->size(), f); fclose(f); }
+    }
     g_cache[key] = out;
     cubin = out;
     log = plog;

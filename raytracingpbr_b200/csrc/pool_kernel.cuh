@@ -52,37 +52,236 @@ struct Pool {
     __device__ __forceinline__ void seti(int f, int slot, int v) { w[f * NSLOT + slot] = (uint32_t)v; }
 };
 
+// A slot's march state is split by who needs it.  Marching needs the ray, t, the step count and the
+// relaxation state; t_eval and idx are rewritten by every march step before anybody reads them.  The resolve
+// phase needs the ray and, families A/B, t_eval (hit position; the argmin is re-evaluated there), family C
+// the marched origin and the argmin.  The step count only feeds the work counters there.
 template <class VAR, int NSLOT>
-__device__ __forceinline__ void load_march(const Pool<NSLOT>& pool, int slot, MarchState& m)
+__device__ __forceinline__ void load_ray_of(const Pool<NSLOT>& pool, int slot, MarchState& m)
 {
     m.ro = V3(pool.getf(F_ROX, slot), pool.getf(F_ROY, slot), pool.getf(F_ROZ, slot));
     m.rd = V3(pool.getf(F_RDX, slot), pool.getf(F_RDY, slot), pool.getf(F_RDZ, slot));
+}
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void load_march(const Pool<NSLOT>& pool, int slot, MarchState& m)
+{
+    load_ray_of<VAR, NSLOT>(pool, slot, m);
     m.t = pool.getf(F_T, slot);
     m.steps = pool.geti(F_STEPS, slot);
-    m.idx = pool.geti(F_IDX, slot);
-    m.t_eval = pool.getf(F_TEVAL, slot);
     if (VAR::MARCHER != MARCH_PLAIN) {
         m.w = pool.getf(F_W, slot); m.s = pool.getf(F_S, slot); m.d = pool.getf(F_D, slot);
-    } else {
-        m.w = 1.0f; m.s = 0.0f; m.d = 0.0f;
     }
 }
 template <class VAR, int NSLOT>
-__device__ __forceinline__ void store_march(Pool<NSLOT>& pool, int slot, const MarchState& m, bool with_ray)
+__device__ __forceinline__ void load_finished(const Pool<NSLOT>& pool, int slot, MarchState& m)
 {
-    if (with_ray || VAR::MARCHER == MARCH_SRC) {
+    load_ray_of<VAR, NSLOT>(pool, slot, m);
+    if (VAR::MARCHER == MARCH_SRC) m.idx = pool.geti(F_IDX, slot);
+    else m.t_eval = pool.getf(F_TEVAL, slot);
+    if (VAR::COUNT) m.steps = pool.geti(F_STEPS, slot);
+}
+// a marching lane parks its slot (the ray itself is already in the slot, except family C's marched origin)
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void store_parked(Pool<NSLOT>& pool, int slot, const MarchState& m)
+{
+    if (VAR::MARCHER == MARCH_SRC) {
         pool.setf(F_ROX, slot, m.ro.x); pool.setf(F_ROY, slot, m.ro.y); pool.setf(F_ROZ, slot, m.ro.z);
-    }
-    if (with_ray) {
-        pool.setf(F_RDX, slot, m.rd.x); pool.setf(F_RDY, slot, m.rd.y); pool.setf(F_RDZ, slot, m.rd.z);
     }
     pool.setf(F_T, slot, m.t);
     pool.seti(F_STEPS, slot, m.steps);
-    pool.seti(F_IDX, slot, m.idx);
-    pool.setf(F_TEVAL, slot, m.t_eval);
     if (VAR::MARCHER != MARCH_PLAIN) {
         pool.setf(F_W, slot, m.w); pool.setf(F_S, slot, m.s); pool.setf(F_D, slot, m.d);
     }
+}
+// a freshly begun bounce (march_begin() state) goes back to the pool
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void store_ready(Pool<NSLOT>& pool, int slot, const MarchState& m)
+{
+    pool.setf(F_ROX, slot, m.ro.x); pool.setf(F_ROY, slot, m.ro.y); pool.setf(F_ROZ, slot, m.ro.z);
+    pool.setf(F_RDX, slot, m.rd.x); pool.setf(F_RDY, slot, m.rd.y); pool.setf(F_RDZ, slot, m.rd.z);
+    pool.setf(F_T, slot, m.t);
+    pool.seti(F_STEPS, slot, m.steps);
+    if (VAR::MARCHER != MARCH_PLAIN) {
+        pool.setf(F_W, slot, m.w); pool.setf(F_S, slot, m.s); pool.setf(F_D, slot, m.d);
+    }
+}
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void store_finished(Pool<NSLOT>& pool, int slot, const MarchState& m, int st)
+{
+    if (VAR::MARCHER == MARCH_SRC) {
+        pool.setf(F_ROX, slot, m.ro.x); pool.setf(F_ROY, slot, m.ro.y); pool.setf(F_ROZ, slot, m.ro.z);
+        pool.seti(F_IDX, slot, m.idx);
+    } else {
+        pool.setf(F_TEVAL, slot, m.t_eval);
+    }
+    if (VAR::COUNT) pool.seti(F_STEPS, slot, m.steps);
+    pool.seti(F_STATUS, slot, st);
+}
+
+// March state of a lane that holds no slot: a ray that stays at (8, 8, 8) -- outside every primitive's
+// expensive region (the neural bunny lives in the unit sphere) -- so the march loop needs no branch around
+// idle lanes; their results are masked out of the vote.  (t stays finite for ~1e36 steps; nothing else of
+// an idle lane's state is ever read.)
+__device__ __forceinline__ void idle_march(MarchState& m)
+{
+    m.ro = V3(8.0f); m.rd = V3(0.0f);
+}
+__device__ __forceinline__ void zero_march(MarchState& m)
+{
+    idle_march(m);
+    m.t = 0.0f; m.w = 1.0f; m.s = 0.0f; m.d = 0.0f; m.t_eval = 0.0f;
+    m.steps = 0; m.idx = 0;
+}
+
+// One resolve batch: every lane with slot >= 0 runs its slot's state machine (surface interaction, sample
+// accumulation, path regeneration, work-queue pull) until the slot needs marching again or dies; slots that
+// are ready to march go on the ready stack.
+template <class VAR, int NSLOT>
+__device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& pool, const int slot, const int lane,
+                                              const unsigned lane_lt, uint8_t* ready, int& n_ready, WorkCounters& cnt)
+{
+    // ---- load the slot
+    Path p;
+    int st = ST_NONE, samp = 0, k = 0;
+    uint32_t pixel = 0;
+    unsigned long long wid = 0;                       // families A/B: work item = scratch index
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);     // family C: the pixel's image_buffer entry
+    zero_march(p.m);
+    p.col = V3(0.f);
+    p.depth = 0;
+    p.rng = rng_make(0u, 0u, 0u);
+    if (slot >= 0) {
+        st = pool.geti(F_STATUS, slot);
+        load_finished<VAR, NSLOT>(pool, slot, p.m);
+        p.col = V3(pool.getf(F_COLX, slot), pool.getf(F_COLY, slot), pool.getf(F_COLZ, slot));
+        p.depth = pool.geti(F_DEPTH, slot);
+        pixel = (uint32_t)pool.geti(F_PIXEL, slot);
+        samp = pool.geti(F_SAMP, slot);
+        k = pool.geti(F_K, slot);
+        p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, (uint32_t)pool.geti(F_RNGN, slot));
+        if (VAR::FAMILY == FAMILY_C)
+            acc = make_float4(pool.getf(F_ACCX, slot), pool.getf(F_ACCY, slot), pool.getf(F_ACCZ, slot),
+                              pool.getf(F_ACCW, slot));
+        else
+            wid = (unsigned long long)(uint32_t)pool.geti(F_ACCX, slot) |
+                  ((unsigned long long)(uint32_t)pool.geti(F_ACCY, slot) << 32);
+    }
+    int pi = (int)(pixel / (uint32_t)P.height), pj = (int)(pixel - (uint32_t)pi * (uint32_t)P.height);
+
+    // ---- run the slot's state machine until it needs marching again (or dies)
+    for (;;) {
+        if (VAR::FAMILY != FAMILY_C) {
+            if (st == ST_HIT) {
+                if (VAR::COUNT) { cnt.normals++; cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                st = (on_hit<VAR>(P, p) && begin_bounce<VAR>(P, p)) ? ST_READY : ST_DONE;
+            } else if (st == ST_MISS) {
+                if (VAR::COUNT) { cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                on_miss<VAR>(P, p);
+                st = ST_DONE;
+            }
+        } else if (st == ST_HIT || st == ST_MISS) {
+            c_after_march<VAR>(P, p, st == ST_HIT ? MARCH_HIT : MARCH_MISS, VAR::COUNT ? &cnt : nullptr);
+            k++;
+            st = ST_ADVANCE;
+        }
+        if (VAR::FAMILY == FAMILY_C) {
+            if (st == ST_ADVANCE) {
+                TaskC task; task.launch = samp; task.k = k;
+                if (c_advance<VAR>(P, pi, pj, p, task, acc, VAR::COUNT ? &cnt : nullptr)) {
+                    st = ST_READY;
+                    k = task.k;
+                } else if (++samp == P.spp) {      // all reference launches replayed: persist the ray
+                    store_ray(P.ray_buffer + (size_t)pixel * 10, p);
+                    P.image_buffer[pixel] = acc;
+                    st = ST_FETCH;
+                } else {
+                    p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, 0u);
+                    k = 0;
+                }
+            }
+        } else if (st == ST_DONE) {
+            P.scratch[wid] = make_float4(p.col.x, p.col.y, p.col.z, 1.0f);   // vec4(ray.color, 1.0)
+            st = ST_FETCH;
+        }
+        // warp-aggregated pull from the global work queue (tile padding is skipped)
+        for (;;) {
+            const unsigned m_fetch = __ballot_sync(kFull, st == ST_FETCH);
+            if (m_fetch == 0u) break;
+            const int leader = __ffs(m_fetch) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m_fetch));
+            base = __shfl_sync(kFull, base, leader);
+            if (st == ST_FETCH) {
+                const unsigned long long wk = base + (unsigned long long)__popc(m_fetch & lane_lt);
+                if (VAR::FAMILY == FAMILY_C) {          // work item = pixel
+                    if (wk >= (unsigned long long)P.total_work) {
+                        st = ST_DEAD;
+                    } else if (work_to_pixel(P, (uint32_t)wk, pi, pj) &&
+                               // src/pathtracer.py:97-101: if diff > NOISE_THRESHOLD: sample(i, j)
+                               (!P.adaptive || P.diff_pixels[pi * P.height + pj] > P.noise_threshold)) {
+                        pixel = (uint32_t)(pi * P.height + pj);
+                        acc = P.image_buffer[pixel];
+                        samp = 0;
+                        k = 0;
+                        load_ray(P.ray_buffer + (size_t)pixel * 10, p);
+                        p.rng = rng_make(pixel, P.sample_base, 0u);
+                        st = ST_ADVANCE;
+                    }
+                } else {                                // work item = (pixel item, sample)
+                    if (wk >= (unsigned long long)P.total_work * (unsigned long long)P.spp) {
+                        st = ST_DEAD;
+                    } else {
+                        const uint32_t item = (uint32_t)(wk / (unsigned long long)P.spp);
+                        if (work_to_pixel(P, item, pi, pj)) {
+                            pixel = (uint32_t)(pi * P.height + pj);
+                            samp = (int)(wk - (unsigned long long)item * (unsigned long long)P.spp);
+                            wid = wk;
+                            st = ST_NEWPATH;
+                        }
+                    }
+                }
+            }
+        }
+        if (VAR::FAMILY != FAMILY_C && st == ST_NEWPATH) {
+            if (VAR::COUNT) cnt.samples++;
+            begin_path<VAR>(P, pixel, pi, pj, P.sample_base + (uint32_t)samp, p);
+            st = begin_bounce<VAR>(P, p) ? ST_READY : ST_DONE;
+        }
+#if defined(RT_JIT_SCENE)
+        // irregular rays (non-finite origin / direction) never enter the specialised march loop
+        if (st == ST_READY && ray_is_irregular(p.m))
+            st = march_to_end_generic<VAR>(P, p.m) == MARCH_HIT ? ST_HIT : ST_MISS;
+        const bool more = st == ST_HIT || st == ST_MISS || (VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE));
+#else
+        const bool more = VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE);
+#endif
+        if (__ballot_sync(kFull, more) == 0u) break;
+    }
+
+    // ---- write the slot back; ready slots go on the ready stack
+    if (slot >= 0) {
+        pool.seti(F_STATUS, slot, st);
+        if (st == ST_READY) {
+            store_ready<VAR, NSLOT>(pool, slot, p.m);
+            pool.setf(F_COLX, slot, p.col.x); pool.setf(F_COLY, slot, p.col.y); pool.setf(F_COLZ, slot, p.col.z);
+            pool.seti(F_DEPTH, slot, p.depth);
+            pool.seti(F_PIXEL, slot, (int)pixel);
+            pool.seti(F_SAMP, slot, samp);
+            pool.seti(F_K, slot, k);
+            pool.seti(F_RNGN, slot, (int)p.rng.n);
+            if (VAR::FAMILY == FAMILY_C) {
+                pool.setf(F_ACCX, slot, acc.x); pool.setf(F_ACCY, slot, acc.y);
+                pool.setf(F_ACCZ, slot, acc.z); pool.setf(F_ACCW, slot, acc.w);
+            } else {
+                pool.seti(F_ACCX, slot, (int)(uint32_t)wid);
+                pool.seti(F_ACCY, slot, (int)(uint32_t)(wid >> 32));
+            }
+        }
+    }
+    const unsigned rdy = __ballot_sync(kFull, slot >= 0 && st == ST_READY);
+    if (slot >= 0 && st == ST_READY) ready[n_ready + __popc(rdy & lane_lt)] = (uint8_t)slot;
+    n_ready += __popc(rdy);
+    __syncwarp();
 }
 
 template <class VAR, int NSLOT>
@@ -106,35 +305,36 @@ __device__ __forceinline__ void pool_body(const KParams& P)
 
     int my = -1;
     MarchState m;
-    m.ro = m.rd = V3(0.f); m.t = m.w = m.s = m.d = m.t_eval = 0.f; m.steps = m.idx = 0;
+    zero_march(m);
     WorkCounters cnt = { 0, 0, 0, 0 };
     unsigned long long c_iters = 0, c_active = 0, c_rounds = 0, c_resolved = 0;
 
-    bool dirty = true;   // warp-uniform: slots changed hands since the last bookkeeping pass
-    unsigned active = 0u;
+    unsigned active = 0u;   // warp-uniform: lanes that hold a slot (my >= 0)
     for (;;) {
-      if (dirty) {
         // ---------------------------------------------------------------- acquire ready slots
-        const unsigned needy = __ballot_sync(kFull, my < 0);
-        if (needy != 0u && n_ready > 0) {
+        // (after a resolve round, or when the refill below ran the ready stack dry earlier)
+        if (active != kFull && n_ready > 0) {
+            const unsigned needy = ~active;
             const int r = __popc(needy & lane_lt);
             if (my < 0 && r < n_ready) {
                 my = ready[n_ready - 1 - r];
                 load_march<VAR, NSLOT>(pool, my, m);
             }
             n_ready -= min(__popc(needy), n_ready);
+            active = __ballot_sync(kFull, my >= 0);
         }
-        active = __ballot_sync(kFull, my >= 0);
 
         // ---------------------------------------------------------------- resolve phase
         if (active != kFull && n_pend > 0 && (n_pend >= P.resolve_min || active == 0u)) {
             if (VAR::COUNT) c_rounds++;
             if (my >= 0) {   // park: the slot stays ready-to-march
-                store_march<VAR, NSLOT>(pool, my, m, false);
+                store_parked<VAR, NSLOT>(pool, my, m);
                 ready[n_ready + __popc(active & lane_lt)] = (uint8_t)my;
                 my = -1;
+                idle_march(m);
             }
             n_ready += __popc(active);
+            active = 0u;
             __syncwarp();
             // One batch always; further batches only while they are full.  A small remainder stays on
             // the pending stack for the next round instead of costing a whole 32-wide pass.
@@ -143,171 +343,46 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                 const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
                 n_pend -= take;
                 if (VAR::COUNT) c_resolved += (unsigned long long)take;
-
-                // ---- load the slot
-                Path p;
-                int st = ST_NONE, samp = 0, k = 0;
-                uint32_t pixel = 0;
-                unsigned long long wid = 0;                       // families A/B: work item = scratch index
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);     // family C: the pixel's image_buffer entry
-                p.m = m;
-                p.col = V3(0.f);
-                p.depth = 0;
-                p.rng = rng_make(0u, 0u, 0u);
-                if (slot >= 0) {
-                    st = pool.geti(F_STATUS, slot);
-                    load_march<VAR, NSLOT>(pool, slot, p.m);
-                    p.col = V3(pool.getf(F_COLX, slot), pool.getf(F_COLY, slot), pool.getf(F_COLZ, slot));
-                    p.depth = pool.geti(F_DEPTH, slot);
-                    pixel = (uint32_t)pool.geti(F_PIXEL, slot);
-                    samp = pool.geti(F_SAMP, slot);
-                    k = pool.geti(F_K, slot);
-                    p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, (uint32_t)pool.geti(F_RNGN, slot));
-                    if (VAR::FAMILY == FAMILY_C)
-                        acc = make_float4(pool.getf(F_ACCX, slot), pool.getf(F_ACCY, slot), pool.getf(F_ACCZ, slot),
-                                          pool.getf(F_ACCW, slot));
-                    else
-                        wid = (unsigned long long)(uint32_t)pool.geti(F_ACCX, slot) |
-                              ((unsigned long long)(uint32_t)pool.geti(F_ACCY, slot) << 32);
-                }
-                int pi = (int)(pixel / (uint32_t)P.height), pj = (int)(pixel - (uint32_t)pi * (uint32_t)P.height);
-
-                // ---- run the slot's state machine until it needs marching again (or dies)
-                for (;;) {
-                    if (VAR::FAMILY != FAMILY_C) {
-                        if (st == ST_HIT) {
-                            if (VAR::COUNT) { cnt.normals++; cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
-                            st = (on_hit<VAR>(P, p) && begin_bounce<VAR>(P, p)) ? ST_READY : ST_DONE;
-                        } else if (st == ST_MISS) {
-                            if (VAR::COUNT) { cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
-                            on_miss<VAR>(P, p);
-                            st = ST_DONE;
-                        }
-                    } else if (st == ST_HIT || st == ST_MISS) {
-                        c_after_march<VAR>(P, p, st == ST_HIT ? MARCH_HIT : MARCH_MISS, VAR::COUNT ? &cnt : nullptr);
-                        k++;
-                        st = ST_ADVANCE;
-                    }
-                    if (VAR::FAMILY == FAMILY_C) {
-                        if (st == ST_ADVANCE) {
-                            TaskC task; task.launch = samp; task.k = k;
-                            if (c_advance<VAR>(P, pi, pj, p, task, acc, VAR::COUNT ? &cnt : nullptr)) {
-                                st = ST_READY;
-                                k = task.k;
-                            } else if (++samp == P.spp) {      // all reference launches replayed: persist the ray
-                                store_ray(P.ray_buffer + (size_t)pixel * 10, p);
-                                P.image_buffer[pixel] = acc;
-                                st = ST_FETCH;
-                            } else {
-                                p.rng = rng_make(pixel, P.sample_base + (uint32_t)samp, 0u);
-                                k = 0;
-                            }
-                        }
-                    } else if (st == ST_DONE) {
-                        P.scratch[wid] = make_float4(p.col.x, p.col.y, p.col.z, 1.0f);   // vec4(ray.color, 1.0)
-                        st = ST_FETCH;
-                    }
-                    // warp-aggregated pull from the global work queue (tile padding is skipped)
-                    for (;;) {
-                        const unsigned m_fetch = __ballot_sync(kFull, st == ST_FETCH);
-                        if (m_fetch == 0u) break;
-                        const int leader = __ffs(m_fetch) - 1;
-                        unsigned long long base = 0;
-                        if (lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m_fetch));
-                        base = __shfl_sync(kFull, base, leader);
-                        if (st == ST_FETCH) {
-                            const unsigned long long wk = base + (unsigned long long)__popc(m_fetch & lane_lt);
-                            if (VAR::FAMILY == FAMILY_C) {          // work item = pixel
-                                if (wk >= (unsigned long long)P.total_work) {
-                                    st = ST_DEAD;
-                                } else if (work_to_pixel(P, (uint32_t)wk, pi, pj) &&
-                                           // src/pathtracer.py:97-101: if diff > NOISE_THRESHOLD: sample(i, j)
-                                           (!P.adaptive || P.diff_pixels[pi * P.height + pj] > P.noise_threshold)) {
-                                    pixel = (uint32_t)(pi * P.height + pj);
-                                    acc = P.image_buffer[pixel];
-                                    samp = 0;
-                                    k = 0;
-                                    load_ray(P.ray_buffer + (size_t)pixel * 10, p);
-                                    p.rng = rng_make(pixel, P.sample_base, 0u);
-                                    st = ST_ADVANCE;
-                                }
-                            } else {                                // work item = (pixel item, sample)
-                                if (wk >= (unsigned long long)P.total_work * (unsigned long long)P.spp) {
-                                    st = ST_DEAD;
-                                } else {
-                                    const uint32_t item = (uint32_t)(wk / (unsigned long long)P.spp);
-                                    if (work_to_pixel(P, item, pi, pj)) {
-                                        pixel = (uint32_t)(pi * P.height + pj);
-                                        samp = (int)(wk - (unsigned long long)item * (unsigned long long)P.spp);
-                                        wid = wk;
-                                        st = ST_NEWPATH;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (VAR::FAMILY != FAMILY_C && st == ST_NEWPATH) {
-                        if (VAR::COUNT) cnt.samples++;
-                        begin_path<VAR>(P, pixel, pi, pj, P.sample_base + (uint32_t)samp, p);
-                        st = begin_bounce<VAR>(P, p) ? ST_READY : ST_DONE;
-                    }
-#if defined(RT_JIT_SCENE)
-                    // irregular rays (non-finite origin / direction) never enter the specialised march loop
-                    if (st == ST_READY && ray_is_irregular(p.m))
-                        st = march_to_end_generic<VAR>(P, p.m) == MARCH_HIT ? ST_HIT : ST_MISS;
-                    const bool more = st == ST_HIT || st == ST_MISS || (VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE));
-#else
-                    const bool more = VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE);
-#endif
-                    if (__ballot_sync(kFull, more) == 0u) break;
-                }
-
-                // ---- write the slot back; ready slots go on the ready stack
-                if (slot >= 0) {
-                    pool.seti(F_STATUS, slot, st);
-                    if (st == ST_READY) {
-                        store_march<VAR, NSLOT>(pool, slot, p.m, true);
-                        pool.setf(F_COLX, slot, p.col.x); pool.setf(F_COLY, slot, p.col.y); pool.setf(F_COLZ, slot, p.col.z);
-                        pool.seti(F_DEPTH, slot, p.depth);
-                        pool.seti(F_PIXEL, slot, (int)pixel);
-                        pool.seti(F_SAMP, slot, samp);
-                        pool.seti(F_K, slot, k);
-                        pool.seti(F_RNGN, slot, (int)p.rng.n);
-                        if (VAR::FAMILY == FAMILY_C) {
-                            pool.setf(F_ACCX, slot, acc.x); pool.setf(F_ACCY, slot, acc.y);
-                            pool.setf(F_ACCZ, slot, acc.z); pool.setf(F_ACCW, slot, acc.w);
-                        } else {
-                            pool.seti(F_ACCX, slot, (int)(uint32_t)wid);
-                            pool.seti(F_ACCY, slot, (int)(uint32_t)(wid >> 32));
-                        }
-                    }
-                }
-                const unsigned rdy = __ballot_sync(kFull, slot >= 0 && st == ST_READY);
-                if (slot >= 0 && st == ST_READY) ready[n_ready + __popc(rdy & lane_lt)] = (uint8_t)slot;
-                n_ready += __popc(rdy);
-                __syncwarp();
+                resolve_batch<VAR, NSLOT>(P, pool, slot, lane, lane_lt, ready, n_ready, cnt);
             } while (n_pend >= 32);
             continue;
         }
         if (active == 0u) break;   // nothing marching, nothing pending, nothing ready: pool drained
-        dirty = false;
-      }
 
-        // ---------------------------------------------------------------- march step
-        if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(active); }
-        int status = MARCH_CONTINUE;
-        if (my >= 0) status = march_step<VAR>(P, m);
-        const unsigned fin = __ballot_sync(kFull, status != MARCH_CONTINUE);
-        if (fin != 0u) {
-            if (status != MARCH_CONTINUE) {
-                store_march<VAR, NSLOT>(pool, my, m, false);
-                pool.seti(F_STATUS, my, status == MARCH_HIT ? ST_HIT : ST_MISS);
-                pend[n_pend + __popc(fin & lane_lt)] = (uint8_t)my;
-                my = -1;
+        // ---------------------------------------------------------------- march loop
+        // One sphere-tracing step per iteration for every lane; lanes without a slot march a harmless
+        // dummy ray (idle_march) and are masked out of the vote, which keeps the loop body branch-free.
+        unsigned fin;
+        float aux;
+        do {
+            if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(active); }
+            const bool f = march_step_fin<VAR>(P, m, aux);
+            fin = __ballot_sync(kFull, f && my >= 0);
+        } while (fin == 0u);
+
+        // ---------------------------------------------------------------- finished lanes: push the slot on the
+        // pending stack and take a ready-to-march one straight away (no extra pass while the ready stack lasts)
+        {
+            const int nf = __popc(fin);
+            if ((fin >> lane) & 1u) {
+                const int r = __popc(fin & lane_lt);
+                store_finished<VAR, NSLOT>(pool, my, m, march_status<VAR>(P, aux) == MARCH_HIT ? ST_HIT : ST_MISS);
+                pend[n_pend + r] = (uint8_t)my;
+                if (r < n_ready) {
+                    my = ready[n_ready - 1 - r];
+                    load_march<VAR, NSLOT>(pool, my, m);
+                } else {
+                    my = -1;
+                    idle_march(m);
+                }
             }
-            n_pend += __popc(fin);
-            active &= ~fin;
-            dirty = true;
+            n_pend += nf;
+            if (nf <= n_ready) {
+                n_ready -= nf;
+            } else {
+                n_ready = 0;
+                active = __ballot_sync(kFull, my >= 0);
+            }
             __syncwarp();
         }
     }
