@@ -42,14 +42,17 @@ enum : int { F_ROX = 0, F_ROY, F_ROZ, F_RDX, F_RDY, F_RDZ, F_COLX, F_COLY, F_COL
              F_STEPS, F_IDX, F_DEPTH, F_RNGN, F_PIXEL, F_SAMP, F_K, F_STATUS, F_ACCX, F_ACCY, F_ACCZ, F_ACCW,
              F_COUNT };
 static_assert(F_COUNT == kPoolSlotWords, "kernels_config.h: kPoolSlotWords");
+// per-warp work-queue chunk (words after the two stacks)
+enum : int { WQ_LO = 0, WQ_HI, WQ_LEFT, WQ_ITEM, WQ_SAMP, WQ_COUNT };
+static_assert(WQ_COUNT <= kPoolQueueWords, "kernels_config.h: kPoolQueueWords");
 
 template <int NSLOT>
 struct Pool {
     uint32_t* w;   // [F_COUNT][NSLOT]
-    __device__ __forceinline__ float getf(int f, int slot) const { return __uint_as_float(w[f * NSLOT + slot]); }
-    __device__ __forceinline__ int geti(int f, int slot) const { return (int)w[f * NSLOT + slot]; }
-    __device__ __forceinline__ void setf(int f, int slot, float v) { w[f * NSLOT + slot] = __float_as_uint(v); }
-    __device__ __forceinline__ void seti(int f, int slot, int v) { w[f * NSLOT + slot] = (uint32_t)v; }
+    __device__ __forceinline__ float getf(int f, int slot) const { return __uint_as_float((w + slot)[f * NSLOT]); }
+    __device__ __forceinline__ int geti(int f, int slot) const { return (int)(w + slot)[f * NSLOT]; }
+    __device__ __forceinline__ void setf(int f, int slot, float v) { (w + slot)[f * NSLOT] = __float_as_uint(v); }
+    __device__ __forceinline__ void seti(int f, int slot, int v) { (w + slot)[f * NSLOT] = (uint32_t)v; }
 };
 
 // A slot's march state is split by who needs it.  Marching needs the ray, t, the step count and the
@@ -138,7 +141,8 @@ __device__ __forceinline__ void zero_march(MarchState& m)
 // are ready to march go on the ready stack.
 template <class VAR, int NSLOT>
 __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& pool, const int slot, const int lane,
-                                              const unsigned lane_lt, uint8_t* ready, int& n_ready, WorkCounters& cnt)
+                                              const unsigned lane_lt, uint8_t* ready, int& n_ready, volatile uint32_t* wq,
+                                              WorkCounters& cnt)
 {
     // ---- load the slot
     Path p;
@@ -203,22 +207,63 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
             P.scratch[wid] = make_float4(p.col.x, p.col.y, p.col.z, 1.0f);   // vec4(ray.color, 1.0)
             st = ST_FETCH;
         }
-        // warp-aggregated pull from the global work queue (tile padding is skipped)
+        // Pull from the work queue (tile padding is skipped).  The warp owns a CHUNK of consecutive work
+        // items (wq[]: next item, items left, and for families A/B the (pixel item, sample) pair of the next
+        // item, so that the 64-bit division happens once per chunk); the global counter is only touched
+        // when the chunk runs out.  Chunk sizes shrink towards the end of the queue (guided scheduling).
         for (;;) {
             const unsigned m_fetch = __ballot_sync(kFull, st == ST_FETCH);
             if (m_fetch == 0u) break;
-            const int leader = __ffs(m_fetch) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m_fetch));
-            base = __shfl_sync(kFull, base, leader);
-            if (st == ST_FETCH) {
-                const unsigned long long wk = base + (unsigned long long)__popc(m_fetch & lane_lt);
+            unsigned left = __shfl_sync(kFull, wq[WQ_LEFT], 0);   // (shfl: provably warp-uniform for the compiler)
+            if (left == 0u) {                                   // warp-uniform
+                const unsigned long long total = VAR::FAMILY == FAMILY_C
+                    ? (unsigned long long)P.total_work : (unsigned long long)P.total_work * (unsigned long long)P.spp;
+                unsigned long long base = 0;
+                unsigned chunk = 0;
+                if (lane == 0) {
+                    const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(P.work_counter);
+                    const unsigned long long rest = total > seen ? total - seen : 0ull;
+                    const unsigned long long fair = rest / ((unsigned long long)(gridDim.x * (blockDim.x >> 5)) * 4ull);
+                    constexpr unsigned kMax = VAR::FAMILY == FAMILY_C ? 32u : 256u;
+                    chunk = fair > (unsigned long long)kMax ? kMax : (fair < 32ull ? 32u : (unsigned)fair);
+                    base = atomicAdd(P.work_counter, (unsigned long long)chunk);
+                    if (base >= total) chunk = 0u;
+                    else if (base + chunk > total) chunk = (unsigned)(total - base);
+                    wq[WQ_LO] = (uint32_t)base; wq[WQ_HI] = (uint32_t)(base >> 32); wq[WQ_LEFT] = chunk;
+                    if (VAR::FAMILY != FAMILY_C && chunk != 0u) {
+                        const unsigned long long item = base / (unsigned long long)P.spp;
+                        wq[WQ_ITEM] = (uint32_t)item;
+                        wq[WQ_SAMP] = (uint32_t)(base - item * (unsigned long long)P.spp);
+                    }
+                }
+                __syncwarp();
+                left = __shfl_sync(kFull, wq[WQ_LEFT], 0);
+                if (left == 0u) {                               // queue exhausted
+                    if (st == ST_FETCH) st = ST_DEAD;
+                    break;
+                }
+            }
+            const unsigned long long cur = (unsigned long long)wq[WQ_LO] | ((unsigned long long)wq[WQ_HI] << 32);
+            const uint32_t item0 = wq[WQ_ITEM], samp0 = wq[WQ_SAMP];
+            const unsigned want = (unsigned)__popc(m_fetch);
+            const unsigned n_take = want < left ? want : left;
+            const unsigned r = (unsigned)__popc(m_fetch & lane_lt);
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned long long nxt = cur + n_take;
+                wq[WQ_LO] = (uint32_t)nxt; wq[WQ_HI] = (uint32_t)(nxt >> 32); wq[WQ_LEFT] = left - n_take;
+                if (VAR::FAMILY != FAMILY_C) {
+                    const uint32_t s2 = samp0 + n_take, q2 = s2 / (uint32_t)P.spp;
+                    wq[WQ_ITEM] = item0 + q2; wq[WQ_SAMP] = s2 - q2 * (uint32_t)P.spp;
+                }
+            }
+            __syncwarp();
+            if (st == ST_FETCH && r < n_take) {
+                const unsigned long long wk = cur + r;
                 if (VAR::FAMILY == FAMILY_C) {          // work item = pixel
-                    if (wk >= (unsigned long long)P.total_work) {
-                        st = ST_DEAD;
-                    } else if (work_to_pixel(P, (uint32_t)wk, pi, pj) &&
-                               // src/pathtracer.py:97-101: if diff > NOISE_THRESHOLD: sample(i, j)
-                               (!P.adaptive || P.diff_pixels[pi * P.height + pj] > P.noise_threshold)) {
+                    if (work_to_pixel(P, (uint32_t)wk, pi, pj) &&
+                        // src/pathtracer.py:97-101: if diff > NOISE_THRESHOLD: sample(i, j)
+                        (!P.adaptive || P.diff_pixels[pi * P.height + pj] > P.noise_threshold)) {
                         pixel = (uint32_t)(pi * P.height + pj);
                         acc = P.image_buffer[pixel];
                         samp = 0;
@@ -228,16 +273,12 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
                         st = ST_ADVANCE;
                     }
                 } else {                                // work item = (pixel item, sample)
-                    if (wk >= (unsigned long long)P.total_work * (unsigned long long)P.spp) {
-                        st = ST_DEAD;
-                    } else {
-                        const uint32_t item = (uint32_t)(wk / (unsigned long long)P.spp);
-                        if (work_to_pixel(P, item, pi, pj)) {
-                            pixel = (uint32_t)(pi * P.height + pj);
-                            samp = (int)(wk - (unsigned long long)item * (unsigned long long)P.spp);
-                            wid = wk;
-                            st = ST_NEWPATH;
-                        }
+                    const uint32_t s1 = samp0 + r, q1 = s1 / (uint32_t)P.spp;
+                    if (work_to_pixel(P, item0 + q1, pi, pj)) {
+                        pixel = (uint32_t)(pi * P.height + pj);
+                        samp = (int)(s1 - q1 * (uint32_t)P.spp);
+                        wid = wk;
+                        st = ST_NEWPATH;
                     }
                 }
             }
@@ -290,12 +331,14 @@ __device__ __forceinline__ void pool_body(const KParams& P)
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lane_lt = (1u << lane) - 1u;
-    constexpr int kWarpWords = F_COUNT * NSLOT + 2 * (NSLOT / 4);
+    constexpr int kWarpWords = F_COUNT * NSLOT + 2 * (NSLOT / 4) + kPoolQueueWords;
     Pool<NSLOT> pool;
     pool.w = smem + warp * kWarpWords;
     uint8_t* ready = reinterpret_cast<uint8_t*>(pool.w + F_COUNT * NSLOT);
     uint8_t* pend = ready + NSLOT;
+    volatile uint32_t* wq = pool.w + F_COUNT * NSLOT + 2 * (NSLOT / 4);   // the warp's chunk of the work queue
     int n_ready = 0, n_pend = NSLOT;          // warp-uniform
+    if (lane < kPoolQueueWords) wq[lane] = 0u;
 
     for (int s = lane; s < NSLOT; s += 32) {
         pool.seti(F_STATUS, s, ST_FETCH);
@@ -343,7 +386,7 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                 const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
                 n_pend -= take;
                 if (VAR::COUNT) c_resolved += (unsigned long long)take;
-                resolve_batch<VAR, NSLOT>(P, pool, slot, lane, lane_lt, ready, n_ready, cnt);
+                resolve_batch<VAR, NSLOT>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt);
             } while (n_pend >= 32);
             continue;
         }

@@ -21,6 +21,7 @@ ap.add_argument("cubin")
 ap.add_argument("--by", default="outer", choices=["outer", "inner"])
 ap.add_argument("--top", type=int, default=50)
 ap.add_argument("--frame", default="pool_kernel.cuh", help="outer attribution: last frame in this file")
+ap.add_argument("--within", default=None, help="file:line -- only instructions inlined under this frame, keyed by the frame just inside it")
 a = ap.parse_args()
 
 rows = list(csv.reader(open(a.sass_csv)))
@@ -56,7 +57,14 @@ agg = collections.defaultdict(lambda: [0, 0, 0])
 tot = [0, 0, 0]
 for (op, fr), r in zip(insts, data):
     e, t, s = int(r[iex]), int(r[ith]), int(r[ism])
-    if a.by == "inner":
+    if a.within:
+        wf, wl = a.within.split(":")
+        pos = [i for i, f in enumerate(fr) if f[0] == wf and f[1] == int(wl)]
+        if not pos:
+            continue
+        i = pos[-1]            # frames are innermost first
+        key = fr[i - 1] if i > 0 else fr[i]
+    elif a.by == "inner":
         key = fr[0] if fr else ("?", 0)
     else:
         cand = [f for f in fr if f[0] == a.frame]
