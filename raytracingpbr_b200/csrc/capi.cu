@@ -363,8 +363,12 @@ static void ensure_jit(RtpbrContext* c)
     std::shared_ptr<std::vector<char>> cubin;
     std::string log;
     const size_t smem = rt::pool_smem_bytes_for(c->jit_block, c->jit_slots);
-    const std::vector<std::string> defs = { "-DRT_POOL_BLOCK=" + std::to_string(c->jit_block), "-DRT_POOL_SLOTS=" + std::to_string(c->jit_slots),
-                                            "-DRT_POOL_MIN_BLOCKS=" + std::to_string(c->jit_min_blocks) };
+    std::vector<std::string> defs = { "-DRT_POOL_BLOCK=" + std::to_string(c->jit_block), "-DRT_POOL_SLOTS=" + std::to_string(c->jit_slots),
+                                      "-DRT_POOL_MIN_BLOCKS=" + std::to_string(c->jit_min_blocks) };
+    if (const char* v = getenv("RTPBR_POOL_MIN_BLOCKS_BUNNY")) {
+        const int x = atoi(v);
+        if (x >= 1 && x <= 16) defs.push_back("-DRT_POOL_MIN_BLOCKS_BUNNY=" + std::to_string(x));
+    }
     if (!rt::jit::compile(src.text, rt::jit::default_include_dir(), cubin, log, defs)) {
         c->jit_enabled = false;
         c->jit_log = "NVRTC failed, using the ahead-of-time kernel: " + log;

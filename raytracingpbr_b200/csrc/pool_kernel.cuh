@@ -353,6 +353,12 @@ __device__ __forceinline__ void pool_body(const KParams& P)
     unsigned long long c_iters = 0, c_active = 0, c_rounds = 0, c_resolved = 0;
 
     unsigned active = 0u;   // warp-uniform: lanes that hold a slot (my >= 0)
+#if defined(RT_JIT_SPLIT_BUNNY)
+    static_assert(VAR::MARCHER == MARCH_ENHANCED && VAR::SHAPESET == SHAPESET_BUNNY, "jit_codegen.h: split march");
+    bool need = false;      // this lane stands at a point whose distance still needs the bunny MLP
+    float cheap = 0.0f;     // ... the minimum over everything else at that point
+    vec3 pb = V3(0.0f);     // ... and the point in the bunny's frame
+#endif
     for (;;) {
         // ---------------------------------------------------------------- acquire ready slots
         // (after a resolve round, or when the refill below ran the ready stack dry earlier)
@@ -372,6 +378,9 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             if (VAR::COUNT) c_rounds++;
             if (my >= 0) {   // park: the slot stays ready-to-march
                 store_parked<VAR, NSLOT>(pool, my, m);
+#if defined(RT_JIT_SPLIT_BUNNY)
+                need = false;   // the pending evaluation is simply redone when the slot marches again
+#endif
                 ready[n_ready + __popc(active & lane_lt)] = (uint8_t)my;
                 my = -1;
                 idle_march(m);
@@ -397,11 +406,36 @@ __device__ __forceinline__ void pool_body(const KParams& P)
         // dummy ray (idle_march) and are masked out of the vote, which keeps the loop body branch-free.
         unsigned fin;
         float aux;
+#if defined(RT_JIT_SPLIT_BUNNY)
+        // Scenes with the neural bunny: a step is cheap outside the bunny's unit sphere (|p| - 0.8 and the
+        // analytic objects) and ~1700 instructions inside (the MLP).  Marching them in lockstep left a third
+        // of the lanes idle during the MLP (ncu: 22.4 of 32 threads active there), so the loop has two
+        // stages: each lane first takes all the cheap steps it can -- until it ends or stands at a point that
+        // needs the MLP -- and then the MLP runs for every marching lane at once.  Per ray the sequence of
+        // evaluations is unchanged; only the interleaving across lanes is.
+        for (;;) {
+            bool f = false;
+            while (my >= 0 && !need && !f) {
+                cheap = jit_nearest_partial(P, at(m.ro, m.rd, m.t), need, pb);
+                if (!need) f = enhanced_advance(P, m, cheap, aux);
+            }
+            fin = __ballot_sync(kFull, f);
+            if (fin != 0u) break;
+            if (need) {
+                const float dist = fminf(cheap, fabsf(sd_bunny_mlp(pb.x, pb.y, pb.z)));
+                need = false;
+                f = enhanced_advance(P, m, dist, aux);
+            }
+            fin = __ballot_sync(kFull, f);
+            if (fin != 0u) break;
+        }
+#else
         do {
             if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(active); }
             const bool f = march_step_fin<VAR>(P, m, aux);
             fin = __ballot_sync(kFull, f && my >= 0);
         } while (fin == 0u);
+#endif
 
         // ---------------------------------------------------------------- finished lanes: push the slot on the
         // pending stack and take a ready-to-march one straight away (no extra pass while the ready stack lasts)
@@ -452,10 +486,15 @@ __device__ __forceinline__ void pool_body(const KParams& P)
 }
 
 
-// The neural bunny keeps ~50 floats live per SDF evaluation: give it 128 registers (2 CTAs / SM).
+// The neural bunny's out-of-line MLP keeps ~50 floats live: its kernels get more registers per thread
+// (fewer resident CTAs) than the analytic scenes.  RT_POOL_MIN_BLOCKS_BUNNY overrides (NVRTC builds: env
+// RTPBR_POOL_MIN_BLOCKS_BUNNY, capi.cu).
+#ifndef RT_POOL_MIN_BLOCKS_BUNNY
+#define RT_POOL_MIN_BLOCKS_BUNNY 2
+#endif
 template <class VAR>
 struct PoolLaunch {
-    static constexpr int kMinBlocks = VAR::SHAPESET == SHAPESET_BUNNY ? 2 : kPoolMinBlocks;
+    static constexpr int kMinBlocks = VAR::SHAPESET == SHAPESET_BUNNY ? RT_POOL_MIN_BLOCKS_BUNNY : kPoolMinBlocks;
 };
 
 template <class VAR, int NSLOT>
