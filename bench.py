@@ -51,8 +51,8 @@ BAND = 4                                 # N > 1: rank = (column / BAND) mod N -
 BYTES_PER_SAMPLE = 16                    # pool kernel: one float4 (radiance, 1) per sample into the scratch buffer
 BYTES_PER_PIXEL_PER_LAUNCH = 32          # simple kernel: vec4 f32 accumulator, 16 B read + 16 B write
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_pathtrace_pool_jit launch at the C1 configuration
-# (ncu --set full, profiles/r01d_ncu_full_k_pathtrace_pool_jit_c1.csv: 66.57 MB read + 1067.82 MB written)
-NCU_TRAFFIC_BYTES_C1 = 66.570240e6 + 1.067819e9
+# (ncu --set full, profiles/r01h_ncu_full_k_pathtrace_pool_jit_c1.csv: 102.34 MB read + 1182.56 MB written)
+NCU_TRAFFIC_BYTES_C1 = 102.339072e6 + 1.182560e9
 FLOP_PER_SCENE_EVAL = 8 * 41             # 8 boxes x 41 flop
 FLOP_PER_NORMAL = 4 * 41
 FLOP_PER_RAY_SHADE = 150
