@@ -220,6 +220,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
                     ? (unsigned long long)P.total_work : (unsigned long long)P.total_work * (unsigned long long)P.spp;
                 unsigned long long base = 0;
                 unsigned chunk = 0;
+                __syncwarp();                                   // every lane has read wq[] before lane 0 rewrites it
                 if (lane == 0) {
                     const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(P.work_counter);
                     const unsigned long long rest = total > seen ? total - seen : 0ull;
@@ -376,6 +377,7 @@ __device__ __forceinline__ void pool_body(const KParams& P)
         // ---------------------------------------------------------------- resolve phase
         if (active != kFull && n_pend > 0 && (n_pend >= P.resolve_min || active == 0u)) {
             if (VAR::COUNT) c_rounds++;
+            __syncwarp();    // the acquire above may have read the stack entries that parking overwrites
             if (my >= 0) {   // park: the slot stays ready-to-march
                 store_parked<VAR, NSLOT>(pool, my, m);
 #if defined(RT_JIT_SPLIT_BUNNY)

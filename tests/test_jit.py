@@ -46,6 +46,15 @@ extern "C" __attribute__((visibility("default"))) int jit_check(const RtpbrConfi
         float b = jit_nearest(P, p, i1);
         out_best[k] = b; out_idx[k] = i1;
         if (memcmp(&a, &b, 4) != 0 || i0 != i1) ++bad;
+#if defined(RT_JIT_SPLIT_BUNNY)
+        // two-stage march of the bunny scenes: cheap part + MLP must reassemble to jit_nearest_dist()
+        bool need; vec3 pb;
+        float c = jit_nearest_partial(P, p, need, pb);
+        if (need) c = fminf(c, fabsf(sd_bunny(pb)));
+        float d = jit_nearest_dist(P, p);
+        if (memcmp(&c, &d, 4) != 0 || memcmp(&a, &d, 4) != 0) ++bad;
+        if (need) ++out_idx[npts];      // how many probe points needed the MLP
+#endif
     }
     return bad;
 }
@@ -68,8 +77,10 @@ def test_generated_nearest_is_bit_identical_on_host(name, tmp_path):
     cu = tmp_path / "jit_check.cu"
     cu.write_text(HARNESS % dict(csrc=csrc, func=body, variant=variant))
     so = tmp_path / "libjit_check.so"
+    split = ["-DRT_JIT_SPLIT_BUNNY=1"] if "jit_nearest_partial" in body else []
+    assert bool(split) == (name == "bunny_glass")
     subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Wno-deprecated-gpu-targets", "-Xcompiler",
-                           "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma,-fvisibility=hidden", "-o", str(so), str(cu)],
+                           "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma,-fvisibility=hidden", "-o", str(so), str(cu)] + split,
                           stderr=subprocess.DEVNULL)
     L = C.CDLL(str(so))
     rng = np.random.default_rng(5)
@@ -78,11 +89,13 @@ def test_generated_nearest_is_bit_identical_on_host(name, tmp_path):
     nat = [o.to_native() for o in objs]
     arr = (N.RtpbrObject * len(nat))(*nat)
     best = np.zeros(len(pts), np.float32)
-    idx = np.zeros(len(pts), np.int32)
+    idx = np.zeros(len(pts) + 1, np.int32)
     bad = L.jit_check(C.byref(cfg), arr, len(nat), 7, pts.ctypes.data_as(C.POINTER(C.c_float)), len(pts),
                       best.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int)))
     assert bad == 0
-    assert len(set(idx.tolist())) >= min(3, len(objs))       # the probe points reach several objects
+    assert len(set(idx[:-1].tolist())) >= min(3, len(objs))  # the probe points reach several objects
+    if split:
+        assert 500 < idx[-1] < len(pts) - 500                # both stages of the split march are exercised
 
 
 def test_specialised_source_drops_zero_terms():
@@ -106,7 +119,7 @@ def test_nvrtc_compiles_the_specialised_kernel(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cornell_box_shortest", "tokyo_ibl", "src_scene"])
+@pytest.mark.parametrize("name", ["cornell_box_shortest", "tokyo_ibl", "src_scene", "bunny_glass"])
 def test_jit_and_aot_kernels_give_the_same_bits(name):
     from raytracingpbr_b200 import PathTracer
     preset = PRESETS[name][0]
