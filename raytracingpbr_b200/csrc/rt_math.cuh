@@ -129,7 +129,16 @@ RT_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
 #endif
 }
 
-RT_HD uint4_rt philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+// RT_RESOLVE_OOL (set by jit_codegen.h for the PBR families): out of line.  Their resolve phase draws from up
+// to six call sites per bounce, and six inlined copies of the ten rounds only bloat a code path that already
+// misses the 32 KB instruction cache (tokyo_ibl: stall_no_instruction 3.0 per issue; +5.5 % with this).  The
+// diffuse-only family A has two call sites and is 1 % faster with the rounds inlined.
+#if defined(RT_RESOLVE_OOL) && defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+RT_HD
+#endif
+uint4_rt philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
