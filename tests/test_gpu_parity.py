@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path (through the C-ABI, include/rtpbr.h) against the CPU
 oracle on the same seeded inputs.  fp32 radiance is required to be BIT-IDENTICAL (rel L2 = 0,
 which is stricter than the 1e-4 relative L2 the north star states; tolerance written below)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -201,6 +203,20 @@ def test_c2_bunny_full_resolution_kernels_agree():
     oc, oo = common.to_oracle(cfg, cam, objs)
     want = po.pathtrace(oc, oo, 2, env=env, i0=500, i1=501)
     assert np.array_equal(a[500], want[500])
+
+
+def test_packed_division_by_1_4_is_ieee_for_every_float(tmp_path):
+    """The bunny's third layer divides by 1.4 with a packed Newton step (rt_integrator.cuh div14_2): checked on the
+    device against `/` for all 2^32 bit patterns."""
+    import subprocess
+    exe = tmp_path / "div14_check"
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-prec-div=true",
+                           "-prec-sqrt=true", "-o", str(exe), os.path.join(common.ROOT, "tests", "native", "div14_check.cu")],
+                          stderr=subprocess.DEVNULL)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    total, fast, bad = (int(x) for x in out.stdout.split())
+    assert out.returncode == 0 and bad == 0, out.stdout
+    assert total == 2 ** 32 and fast == 2 * 201 * 2 ** 23     # exponent fields 27..227, both signs
 
 
 def test_c4_resolution_4096_sharded_property():
