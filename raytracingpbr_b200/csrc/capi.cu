@@ -359,7 +359,9 @@ static void ensure_jit(RtpbrContext* c)
     c->jit_stale = false;
     c->jit_kernel.reset();
     if (c->cfg.count_work) { c->jit_log = "disabled: count_work uses the ahead-of-time counting kernel"; return; }
-    const rt::jit::Source src = rt::jit::generate(c->cfg, c->scene.data(), (int)c->scene.size());
+    int max_pairs = 1 << 30;      // RTPBR_JIT_PAIRS: how many box pairs use the packed f32x2 form (tuning knob)
+    if (const char* v = getenv("RTPBR_JIT_PAIRS")) max_pairs = atoi(v) < 0 ? 0 : atoi(v);
+    const rt::jit::Source src = rt::jit::generate(c->cfg, c->scene.data(), (int)c->scene.size(), max_pairs);
     std::shared_ptr<std::vector<char>> cubin;
     std::string log;
     const size_t smem = rt::pool_smem_bytes_for(c->jit_block, c->jit_slots);
