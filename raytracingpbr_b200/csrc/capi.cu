@@ -386,7 +386,7 @@ static void ensure_jit(RtpbrContext* c)
         fprintf(stderr, "librtpbr: %s\n", c->jit_log.c_str());
         return;
     }
-    c->jit_log = "scene-specialised kernel active (" + std::to_string(k->registers) + " registers, " +
+    c->jit_log = "scene-specialised kernel active (NVRTC " + rt::jit::nvrtc_version() + ", " + std::to_string(k->registers) + " registers, " +
                  std::to_string(c->jit_blocks_per_sm) + " CTAs/SM x " + std::to_string(c->jit_block) + " threads, " +
                  std::to_string(c->jit_slots) + " slots/warp)";
     c->jit_kernel = std::move(k);

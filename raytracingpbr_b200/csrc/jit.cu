@@ -37,6 +37,7 @@ struct Driver {
     int (*GetErrorString)(int, const char**) = nullptr;
 };
 Nvrtc g_nvrtc;
+int g_nvrtc_major = 0, g_nvrtc_minor = 0;
 Driver g_drv;
 std::mutex g_mu;
 std::unordered_map<std::string, std::shared_ptr<std::vector<char>>> g_cache;
@@ -51,7 +52,16 @@ bool sym(void* h, const char* name, F& f)
 bool load_nvrtc(std::string& why)
 {
     if (g_nvrtc.h) return true;
-    const char* names[] = { getenv("RTPBR_NVRTC_LIB"), "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so" };
+    // The toolkit's own NVRTC first, by absolute path.  A bare soname resolves to whatever copy the process has
+    // already mapped -- with PyTorch imported that is the NVRTC 12.8 bundled in its wheels, whose code for the
+    // specialised march loop is 5.5 % slower than 12.9's (measured: 70.5 vs 66.8 ms per C1 launch; that, not NCCL,
+    // was the per-rank slowdown of the multi-GPU bench).
+#if defined(RTPBR_NVRTC_DIR)
+    const char* built_with = RTPBR_NVRTC_DIR "/libnvrtc.so.12";
+#else
+    const char* built_with = nullptr;
+#endif
+    const char* names[] = { getenv("RTPBR_NVRTC_LIB"), built_with, "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so" };
     void* h = nullptr;
     for (const char* n : names) {
         if (!n || !*n) continue;
@@ -67,6 +77,8 @@ bool load_nvrtc(std::string& why)
     if (!ok) { why = "libnvrtc is missing required symbols"; return false; }
     n.h = h;
     g_nvrtc = n;
+    int (*version)(int*, int*) = nullptr;
+    if (sym(h, "nvrtcVersion", version)) version(&g_nvrtc_major, &g_nvrtc_minor);
     return true;
 }
 
@@ -99,6 +111,11 @@ std::string drv_err(const char* what, int rc)
 Kernel::~Kernel()
 {
     if (module && g_drv.ModuleUnload) g_drv.ModuleUnload(module);
+}
+
+std::string nvrtc_version()
+{
+    return g_nvrtc.h ? std::to_string(g_nvrtc_major) + "." + std::to_string(g_nvrtc_minor) : std::string("not loaded");
 }
 
 std::string default_include_dir()

@@ -29,6 +29,8 @@ bool occupancy(const Kernel& k, int block, size_t dynamic_smem, int* blocks_per_
 bool launch(const Kernel& k, const KParams& P, int grid, int block, size_t dynamic_smem, cudaStream_t stream, std::string& err);
 // Directory of this shared library + "/csrc".
 std::string default_include_dir();
+// "12.9" once NVRTC has been loaded (which copy gets loaded matters: see load_nvrtc in jit.cu)
+std::string nvrtc_version();
 
 }  // namespace jit
 }  // namespace rt

@@ -118,6 +118,26 @@ def test_nvrtc_compiles_the_specialised_kernel(name):
         raise
 
 
+def test_specialised_kernel_does_not_depend_on_who_loaded_an_nvrtc_first(tmp_path):
+    """PyTorch wheels bundle their own (older) libnvrtc.so.12; once torch is imported a bare-soname dlopen would pick
+    that copy and the specialised kernel came out 5.5 % slower on the multi-GPU bench.  jit.cu loads the toolkit's
+    NVRTC by absolute path: the cubin must be byte-identical with and without torch in the process."""
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n%s"
+            "from raytracingpbr_b200 import _native as N, scenes\n"
+            "cfg, objs, cam, tm = scenes.cornell_box_shortest(64, 64, max_bounces=8)\n"
+            "N.jit_compile_check(cfg, [o.to_native() for o in objs])\n")
+    cubins = []
+    for tag, pre in (("plain", ""), ("torch", "import torch\n")):
+        env = dict(os.environ, RTPBR_JIT_DUMP=str(tmp_path / tag))
+        r = subprocess.run([sys.executable, "-c", code % (common.ROOT, pre)], env=env, capture_output=True, text=True)
+        if r.returncode != 0 and "dlopen" in r.stderr:
+            pytest.skip("NVRTC not available on this machine")
+        assert r.returncode == 0, r.stderr[-2000:]
+        cubins.append((tmp_path / (tag + ".cubin")).read_bytes())
+    assert cubins[0] == cubins[1]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cornell_box_shortest", "tokyo_ibl", "src_scene", "bunny_glass"])
 def test_jit_and_aot_kernels_give_the_same_bits(name):
