@@ -432,11 +432,21 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             if (fin != 0u) break;
         }
 #else
+#if defined(RT_MARCH_VOTE_EVERY_2)
+        // tuning knob (RTPBR_MARCH_UNROLL=2): vote after every second step; a lane whose march ends on the first
+        // one sits the second one out
+        do {
+            bool f = march_step_fin<VAR>(P, m, aux);
+            if (!f) f = march_step_fin<VAR>(P, m, aux);
+            fin = __ballot_sync(kFull, f && my >= 0);
+        } while (fin == 0u);
+#else
         do {
             if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(active); }
             const bool f = march_step_fin<VAR>(P, m, aux);
             fin = __ballot_sync(kFull, f && my >= 0);
         } while (fin == 0u);
+#endif
 #endif
 
         // ---------------------------------------------------------------- finished lanes: push the slot on the
