@@ -70,6 +70,28 @@ def test_scratch_chunking_is_invisible(monkeypatch):
     assert np.array_equal(render(256, 256, 5, 8, seed=3), want)
 
 
+@pytest.mark.parametrize("knobs", [
+    {"RTPBR_JIT_PAIRS": "1"}, {"RTPBR_JIT_PAIRS": "0"}, {"RTPBR_PACK_CLAMPS": "4"}, {"RTPBR_ALU_CLAMPS": "2"},
+    {"RTPBR_MARCH_UNROLL": "2"}, {"RTPBR_POOL_SLOTS": "32", "RTPBR_RESOLVE_MIN": "1"}, {"RTPBR_POOL_SLOTS": "96", "RTPBR_POOL_BLOCK": "128"},
+    {"RTPBR_PACK_CLAMPS": "2", "RTPBR_ALU_CLAMPS": "1", "RTPBR_MARCH_UNROLL": "2", "RTPBR_POOL_MIN_BLOCKS": "3"},
+], ids=lambda k: ",".join(f"{a[6:]}={b}" for a, b in k.items()))
+def test_tuning_knobs_do_not_change_a_bit(monkeypatch, knobs):
+    # code-shape and pool-geometry knobs of the specialised kernel
+    want = oracle(112, 72, 6, 8, seed=5)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    cfg, objs, cam, tm = scenes.cornell_box_shortest(112, 72, max_bounces=8, seed=5)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.refresh()
+        pt.pathtrace(6)
+        got = pt.image_buffer.to_numpy()
+        active, msg = pt.ctx.jit_status()
+    if not active and "dlopen" in msg:
+        pytest.skip("NVRTC not available on this machine: " + msg)
+    assert active, msg
+    assert np.array_equal(got, want)
+
+
 def test_work_counters_match_oracle():
     got, cnt = render(128, 96, 3, 8, seed=4, count=True)
     want, ocnt = oracle(128, 96, 3, 8, seed=4, counters=True)
