@@ -68,26 +68,49 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every 10 ms from a
+    thread (nvidia_ml_py); falls back to spawning nvidia-smi (~0.15 s per sample) when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._stop = index, [], threading.Event()   # rows: (sm_mhz, sm_max_mhz, watts, reason bitmask)
+        self._nvml = self._handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml, self._handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self._nvml = None
+        self.source = "nvml" if self._nvml else "nvidia-smi"
         self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._handle
+        self.rows.append((float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)),
+                          n.nvmlDeviceGetPowerUsage(h) / 1000.0, int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [s.strip() for s in out.strip().split(",")]
+        if len(parts) >= 7:
+            mask = sum(bit for k, (_, bit) in enumerate(self.BITS) if parts[3 + k].lower().startswith("active"))
+            self.rows.append((float(parts[0]), float(parts[1]), float(parts[2]), mask))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self._stop.wait(0.1)
+                if self._nvml:          # NVML call failed: switch to nvidia-smi for the rest of the run
+                    self._nvml, self.source = None, "nvidia-smi"
+            self._stop.wait(0.01 if self._nvml else 0.1)
 
     def start(self):
         self._t.start()
@@ -96,12 +119,11 @@ class ClockSampler:
         self._stop.set()
         self._t.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [name for name, bit in self.BITS if any(r[3] & bit for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.rows[0][1], "reasons": reasons,
+                "power_w_max": max(r[2] for r in self.rows), "samples": len(self.rows), "source": self.source}
 
 
 # ------------------------------------------------------------------------------ CPU legs

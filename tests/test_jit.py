@@ -106,6 +106,24 @@ def test_specialised_source_drops_zero_terms():
     assert "P.geom" not in body                                               # no parameter-block loads in the march loop
 
 
+def test_specialised_source_carries_the_right_variant_switches():
+    """march constants as literals everywhere; out-of-line resolve helpers for the PBR families without the bunny;
+    the two-stage march loop for bunny scenes with the enhanced marcher (jit_codegen.h)."""
+    def src_of(preset):
+        cfg, objs, _, _ = preset(32, 32)
+        return N.jit_source(cfg, [o.to_native() for o in objs]), cfg
+    a, cfg = src_of(scenes.cornell_box_shortest)
+    assert "#define RT_K_MAX_STEPS %d\n" % cfg.max_steps in a and "#define RT_K_HIT_EPS" in a and "#define RT_K_T_FAR" in a
+    assert "RT_RESOLVE_OOL" not in a and "RT_JIT_SPLIT_BUNNY" not in a and "jit_nearest_partial" not in a
+    assert a.count("sd_box2_ranged_x2<false>") == 8                      # 4 packed pairs x (jit_nearest, jit_nearest_dist)
+    for preset in (scenes.tokyo_ibl, scenes.cornell_box, scenes.cornell_box_v3, scenes.src_scene):
+        b, _ = src_of(preset)
+        assert "#define RT_RESOLVE_OOL 1" in b and "RT_JIT_SPLIT_BUNNY" not in b
+    c, _ = src_of(scenes.bunny_glass)
+    assert "#define RT_JIT_SPLIT_BUNNY 1" in c and "RT_RESOLVE_OOL" not in c
+    assert "jit_nearest_partial(const KParams& P, vec3 pos, bool& need_mlp, vec3& pb)" in c and "rt_inf()" in c
+
+
 @pytest.mark.parametrize("name", list(PRESETS))
 def test_nvrtc_compiles_the_specialised_kernel(name):
     preset = PRESETS[name][0]
