@@ -19,15 +19,20 @@ constexpr unsigned kFull = 0xffffffffu;
 // granularity is a single path (no ragged tail: 67 M items on C1).  Family C: a slot is a pixel
 // worker, because its launches are sequentially dependent through ray_buffer.
 //
-// The warp alternates between two phases, both at (nearly) full lane occupancy:
+// The warp alternates between phases, all at (nearly) full lane occupancy:
 //   MARCH    each lane holds the march state of one slot in registers and the warp-wide loop
-//            body is ONE sphere-tracing step (scene SDF evaluation).  A lane whose ray hits /
-//            leaves / runs out of steps writes the result to its slot, pushes the slot on the
-//            warp's `pending` stack and pops a ready-to-march slot from the `ready` stack.
+//            body is ONE sphere-tracing step (scene SDF evaluation) followed by one vote: "did
+//            any lane's march end?".  Nothing else lives in the loop -- how a march ended is
+//            decided afterwards (march_status), lanes without a slot march a harmless dummy ray
+//            and are masked out of the vote (idle_march), constants are literals in the
+//            specialised kernels.  (Bunny scenes: two stages per iteration, see pool_body.)
+//   FINISH   the lanes whose march ended write t_eval + status to their slots, push them on the
+//   + REFILL warp's `pending` stack and pop ready-to-march slots from the `ready` stack right
+//            there (ballot + popc ranks, no atomics); the loop is re-entered directly.
 //   RESOLVE  when lanes would idle (ready stack empty) the marching lanes park their slots and
-//            all 32 lanes pop pending slots: surface interaction (normal, BSDF sample,
-//            Russian roulette), sample accumulation, path regeneration, and warp-aggregated
-//            work-queue pulls.  Resolved slots go back on the ready stack.
+//            all 32 lanes pop pending slots (resolve_batch): surface interaction (normal, BSDF
+//            sample, Russian roulette), sample output, path regeneration, and pulls from the
+//            warp's chunk of the work queue.  Resolved slots go back on the ready stack.
 // With NSLOT = 64 the pool holds 32 marching + 32 ready/pending slots, so the heavy-tailed
 // march lengths (p50 28, p99 ~100 steps) no longer idle lanes, and the divergent shading code
 // runs on compacted batches.  The RNG is keyed by (pixel, sample, draw index) only, so the
