@@ -98,6 +98,58 @@ def test_generated_nearest_is_bit_identical_on_host(name, tmp_path):
         assert 500 < idx[-1] < len(pts) - 500                # both stages of the split march are exercised
 
 
+def _check_on_host(cfg, objs, variant, extent, tmp_path, tag):
+    src, body = specialised_function(cfg, objs)
+    csrc = os.path.join(common.ROOT, "raytracingpbr_b200", "csrc")
+    cu = tmp_path / f"jit_check_{tag}.cu"
+    cu.write_text(HARNESS % dict(csrc=csrc, func=body, variant=variant))
+    so = tmp_path / f"libjit_check_{tag}.so"
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Wno-deprecated-gpu-targets", "-Xcompiler",
+                           "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma,-fvisibility=hidden", "-o", str(so), str(cu)],
+                          stderr=subprocess.DEVNULL)
+    L = C.CDLL(str(so))
+    rng = np.random.default_rng(17)
+    pts = np.concatenate([rng.uniform(-extent, extent, (3000, 3)), rng.normal(size=(1000, 3)) * extent * 0.3]).astype(np.float32)
+    pts[:4] = 0.0
+    for k, o in enumerate(objs[:16]):                      # points exactly on object centres and axes
+        pts[4 + k] = np.asarray(o.transform.position, np.float32)
+    nat = [o.to_native() for o in objs]
+    arr = (N.RtpbrObject * len(nat))(*nat)
+    best = np.zeros(len(pts), np.float32)
+    idx = np.zeros(len(pts) + 1, np.int32)
+    return L.jit_check(C.byref(cfg), arr, len(nat), 3, pts.ctypes.data_as(C.POINTER(C.c_float)), len(pts),
+                       best.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int))), src
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_generated_nearest_on_random_scenes(seed, tmp_path):
+    """The exactness claims of jit_codegen.h (elided zero / unit matrix terms, ranged sqrt, packed pairs, doubled
+    distances) on scenes nobody tuned: random primitives, rotations drawn from a mix of arbitrary angles and
+    multiples of 90 degrees, zero and non-zero offsets, tiny and large extents."""
+    from raytracingpbr_b200.dataclass import Material, SDFObject, Transform
+    from raytracingpbr_b200.tmath import vec3
+    rng = np.random.default_rng(seed)
+    cfg, _, _, _ = scenes.tokyo_ibl(32, 32)               # family B, analytic shape set, enhanced marcher
+    objs = []
+    for _ in range(int(rng.integers(3, 13))):
+        angles = [float(rng.choice([0.0, 90.0, -90.0, 180.0, 270.0, rng.uniform(-360, 360)])) for _ in range(3)]
+        pos = [float(rng.choice([0.0, rng.uniform(-2, 2)])) for _ in range(3)]
+        scale = [float(rng.choice([1.0, 0.5, rng.uniform(0.01, 1.5), 1e-9, 3e4])) for _ in range(3)]
+        kind = int(rng.choice([scenes.SHAPE_SPHERE, scenes.SHAPE_BOX, scenes.SHAPE_BOX, scenes.SHAPE_BOX, scenes.SHAPE_CYLINDER,
+                               scenes.SHAPE_CONE, scenes.SHAPE_PLANE]))
+        objs.append(SDFObject(type=kind, transform=Transform(vec3(*pos), vec3(*angles), vec3(*scale)),
+                              material=Material(vec3(0.5), vec3(1), 0.5, 0.0, 0.0, 1.5)))
+    bad, src = _check_on_host(cfg, objs, "Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_ENHANCED, false>", 3.0, tmp_path, f"rand{seed}")
+    assert bad == 0
+    # family A on random boxes only (sharp boxes, first object seeds the minimum)
+    cfg_a, _, _, _ = scenes.cornell_box_shortest(32, 32)
+    boxes = [o for o in objs if o.type == scenes.SHAPE_BOX] or objs[:1]
+    for o in boxes:
+        o.type = scenes.SHAPE_BOX
+    bad, _ = _check_on_host(cfg_a, boxes, "Variant<FAMILY_A, 0, SHAPESET_BOX, MARCH_PLAIN, false>", 3.0, tmp_path, f"randA{seed}")
+    assert bad == 0
+
+
 def test_specialised_source_drops_zero_terms():
     cfg, objs, _, _ = scenes.cornell_box_shortest(32, 32)
     src, body = specialised_function(cfg, objs)
@@ -157,7 +209,7 @@ def test_specialised_kernel_does_not_depend_on_who_loaded_an_nvrtc_first(tmp_pat
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cornell_box_shortest", "tokyo_ibl", "src_scene", "bunny_glass"])
+@pytest.mark.parametrize("name", list(PRESETS))
 def test_jit_and_aot_kernels_give_the_same_bits(name):
     from raytracingpbr_b200 import PathTracer
     preset = PRESETS[name][0]
