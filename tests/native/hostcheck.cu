@@ -78,4 +78,17 @@ HC_API void hostcheck_sincos(float x, float* s, float* c) { sincos_rt(x, *s, *c)
 HC_API float hostcheck_atan2(float y, float x) { return atan2_rt(y, x); }
 HC_API float hostcheck_asin(float x) { return asin_rt(x); }
 HC_API void hostcheck_euler(const float rot_deg[3], float out9[9]) { euler_matrix_deg(rot_deg, out9); }
+// three draws starting at draw n of stream (pixel, launch): out[0..2] by three rng_next calls, out[3..5] by
+// rng_next2_ahead followed by rng_next (the order on_hit + begin_bounce use); out[6] = draws consumed by each
+HC_API void hostcheck_rng3(uint32_t seed, uint32_t pixel, uint32_t launch, uint32_t n, float out[7])
+{
+    KParams P;
+    memset(&P, 0, sizeof(P));
+    P.seed = seed;
+    Rng a = rng_make(pixel, launch, n), b = rng_make(pixel, launch, n);
+    out[0] = rng_next(P, a); out[1] = rng_next(P, a); out[2] = rng_next(P, a);
+    rng_next2_ahead(P, b, out[3], out[4]);
+    out[5] = rng_next(P, b);
+    out[6] = (a.n == n + 3u && b.n == n + 3u) ? 3.0f : -1.0f;
+}
 HC_API float hostcheck_sd_bunny(const float p[3]) { return sd_bunny(V3(p[0], p[1], p[2])); }

@@ -6,6 +6,7 @@ import math
 import numpy as np
 import pytest
 
+import common
 from common import po
 
 
@@ -207,3 +208,26 @@ def test_white_furnace_radiance_is_bounded():
     mean = img[..., :3] / img[..., 3:]
     # camera sits outside the box front (open side): escaping paths are black, inside ones <= 1
     assert mean.max() <= 1.0 + 1e-6 and mean.min() >= 0.0
+
+
+def test_two_ahead_draws_are_the_same_stream():
+    """rng_next2_ahead (hit shading of family A) returns exactly the numbers three rng_next calls return, for every
+    position of the draws inside a Philox block, and matches the oracle's stream."""
+    import ctypes as C
+    L = common.hostcheck()
+    L.hostcheck_rng3.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_float)]
+    L.hostcheck_rng3.restype = None
+    rng = np.random.default_rng(3)
+    out = (C.c_float * 7)()
+    for n in list(range(0, 12)) + [int(x) for x in rng.integers(0, 2 ** 20, 40)]:
+        seed, pixel, launch = (int(x) for x in rng.integers(0, 2 ** 32, 3, dtype=np.uint64))
+        L.hostcheck_rng3(seed, pixel, launch, n, out)
+        v = np.frombuffer(out, dtype=np.float32).copy()
+        assert v[6] == 3.0
+        assert np.array_equal(v[0:3].view(np.uint32), v[3:6].view(np.uint32)), (n, v)
+        want = []
+        for k in range(3):                                   # the oracle's Philox + Taichi's u32 -> f32 rule
+            raw = (C.c_uint32 * 4)()
+            po.lib().orc_philox4x32_10((C.c_uint32 * 4)(pixel, launch, (n + k) >> 2, 0), (C.c_uint32 * 2)(seed, 0x52545042), raw)
+            want.append(np.float32(raw[(n + k) & 3] >> 8) * np.float32(2.0 ** -24))
+        assert np.array_equal(np.asarray(want, np.float32).view(np.uint32), v[0:3].view(np.uint32))
