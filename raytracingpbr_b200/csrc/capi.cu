@@ -367,6 +367,10 @@ static void ensure_jit(RtpbrContext* c)
     const size_t smem = rt::pool_smem_bytes_for(c->jit_block, c->jit_slots);
     std::vector<std::string> defs = { "-DRT_POOL_BLOCK=" + std::to_string(c->jit_block), "-DRT_POOL_SLOTS=" + std::to_string(c->jit_slots),
                                       "-DRT_POOL_MIN_BLOCKS=" + std::to_string(c->jit_min_blocks) };
+    if (const char* v = getenv("RTPBR_REGEN_MIN")) {
+        const int x = atoi(v);
+        if (x >= 1 && x <= 32) defs.push_back("-DRT_REGEN_MIN=" + std::to_string(x));
+    }
     if (const char* v = getenv("RTPBR_MARCH_UNROLL")) {
         if (atoi(v) == 2) defs.push_back("-DRT_MARCH_VOTE_EVERY_2=1");
     }

@@ -48,7 +48,7 @@ enum : int { F_ROX = 0, F_ROY, F_ROZ, F_RDX, F_RDY, F_RDZ, F_COLX, F_COLY, F_COL
              F_COUNT };
 static_assert(F_COUNT == kPoolSlotWords, "kernels_config.h: kPoolSlotWords");
 // per-warp work-queue chunk (words after the two stacks)
-enum : int { WQ_LO = 0, WQ_HI, WQ_LEFT, WQ_ITEM, WQ_SAMP, WQ_COUNT };
+enum : int { WQ_LO = 0, WQ_HI, WQ_LEFT, WQ_ITEM, WQ_SAMP, WQ_NFRESH, WQ_COUNT };
 static_assert(WQ_COUNT <= kPoolQueueWords, "kernels_config.h: kPoolQueueWords");
 
 template <int NSLOT>
@@ -144,10 +144,19 @@ __device__ __forceinline__ void zero_march(MarchState& m)
 // One resolve batch: every lane with slot >= 0 runs its slot's state machine (surface interaction, sample
 // accumulation, path regeneration, work-queue pull) until the slot needs marching again or dies; slots that
 // are ready to march go on the ready stack.
-template <class VAR, int NSLOT>
+// RT_REGEN_MIN > 0 (experiment, families A/B; NVRTC builds: env RTPBR_REGEN_MIN): path regeneration leaves the
+// hit / miss batches.  A slot whose path ended goes on a third stack (`fresh`) and regeneration batches run only when
+// RT_REGEN_MIN slots wait there or lanes would idle, so that fetch + camera ray + first roulette run at ~25 instead
+// of ~8 lanes.  MODE_HITS batches never fetch, MODE_FRESH batches only fetch and start paths.
+#ifndef RT_REGEN_MIN
+#define RT_REGEN_MIN 0
+#endif
+enum : int { MODE_ALL = 0, MODE_HITS = 1, MODE_FRESH = 2 };
+
+template <class VAR, int NSLOT, int MODE = MODE_ALL>
 __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& pool, const int slot, const int lane,
                                               const unsigned lane_lt, uint8_t* ready, int& n_ready, volatile uint32_t* wq,
-                                              WorkCounters& cnt)
+                                              WorkCounters& cnt, uint8_t* pend = nullptr, int* n_pend = nullptr, uint8_t* fresh = nullptr)
 {
     // ---- load the slot
     Path p;
@@ -179,7 +188,9 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
 
     // ---- run the slot's state machine until it needs marching again (or dies)
     for (;;) {
-        if (VAR::FAMILY != FAMILY_C) {
+        if (MODE == MODE_FRESH) {
+            // regeneration batches carry no marched rays
+        } else if (VAR::FAMILY != FAMILY_C) {
             if (st == ST_HIT) {
                 if (VAR::COUNT) { cnt.normals++; cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
                 st = (on_hit<VAR>(P, p) && begin_bounce<VAR>(P, p)) ? ST_READY : ST_DONE;
@@ -217,6 +228,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
         // item, so that the 64-bit division happens once per chunk); the global counter is only touched
         // when the chunk runs out.  Chunk sizes shrink towards the end of the queue (guided scheduling).
         for (;;) {
+            if (MODE == MODE_HITS) break;                       // ended paths wait on the fresh stack
             const unsigned m_fetch = __ballot_sync(kFull, st == ST_FETCH);
             if (m_fetch == 0u) break;
             unsigned left = __shfl_sync(kFull, wq[WQ_LEFT], 0);   // (shfl: provably warp-uniform for the compiler)
@@ -289,7 +301,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
                 }
             }
         }
-        if (VAR::FAMILY != FAMILY_C && st == ST_NEWPATH) {
+        if (MODE != MODE_HITS && VAR::FAMILY != FAMILY_C && st == ST_NEWPATH) {
             if (VAR::COUNT) cnt.samples++;
             begin_path<VAR>(P, pixel, pi, pj, P.sample_base + (uint32_t)samp, p);
             st = begin_bounce<VAR>(P, p) ? ST_READY : ST_DONE;
@@ -298,9 +310,13 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
         // irregular rays (non-finite origin / direction) never enter the specialised march loop
         if (st == ST_READY && ray_is_irregular(p.m))
             st = march_to_end_generic<VAR>(P, p.m) == MARCH_HIT ? ST_HIT : ST_MISS;
-        const bool more = st == ST_HIT || st == ST_MISS || (VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE));
+        const bool more = MODE == MODE_FRESH ? (st == ST_DONE || st == ST_FETCH)       // (irregular new rays go to the pending stack)
+                        : MODE == MODE_HITS  ? (st == ST_HIT || st == ST_MISS || st == ST_DONE)
+                        : st == ST_HIT || st == ST_MISS || (VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE));
 #else
-        const bool more = VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE);
+        const bool more = MODE == MODE_FRESH ? (st == ST_DONE || st == ST_FETCH)
+                        : MODE == MODE_HITS  ? (st == ST_DONE)
+                        : VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE);
 #endif
         if (__ballot_sync(kFull, more) == 0u) break;
     }
@@ -308,7 +324,9 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
     // ---- write the slot back; ready slots go on the ready stack
     if (slot >= 0) {
         pool.seti(F_STATUS, slot, st);
-        if (st == ST_READY) {
+        const bool marched_here = MODE == MODE_FRESH && (st == ST_HIT || st == ST_MISS);   // irregular new ray, marched by the generic code
+        if (marched_here) pool.setf(F_TEVAL, slot, p.m.t_eval);
+        if (st == ST_READY || marched_here) {
             store_ready<VAR, NSLOT>(pool, slot, p.m);
             pool.setf(F_COLX, slot, p.col.x); pool.setf(F_COLY, slot, p.col.y); pool.setf(F_COLZ, slot, p.col.z);
             pool.seti(F_DEPTH, slot, p.depth);
@@ -328,6 +346,18 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
     const unsigned rdy = __ballot_sync(kFull, slot >= 0 && st == ST_READY);
     if (slot >= 0 && st == ST_READY) ready[n_ready + __popc(rdy & lane_lt)] = (uint8_t)slot;
     n_ready += __popc(rdy);
+    if (MODE == MODE_HITS) {          // ended paths: onto the fresh stack
+        const unsigned fr = __ballot_sync(kFull, slot >= 0 && st == ST_FETCH);
+        const int n_fresh = (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
+        if (slot >= 0 && st == ST_FETCH) fresh[n_fresh + __popc(fr & lane_lt)] = (uint8_t)slot;
+        __syncwarp();
+        if (lane == 0) wq[WQ_NFRESH] = (uint32_t)(n_fresh + __popc(fr));
+    }
+    if (MODE == MODE_FRESH) {         // irregular new rays were marched right here: they need a hit / miss batch
+        const unsigned hm = __ballot_sync(kFull, slot >= 0 && (st == ST_HIT || st == ST_MISS));
+        if (slot >= 0 && (st == ST_HIT || st == ST_MISS)) pend[*n_pend + __popc(hm & lane_lt)] = (uint8_t)slot;
+        *n_pend += __popc(hm);
+    }
     __syncwarp();
 }
 
@@ -337,18 +367,20 @@ __device__ __forceinline__ void pool_body(const KParams& P)
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lane_lt = (1u << lane) - 1u;
-    constexpr int kWarpWords = F_COUNT * NSLOT + 2 * (NSLOT / 4) + kPoolQueueWords;
+    constexpr int kWarpWords = F_COUNT * NSLOT + kPoolStacks * (NSLOT / 4) + kPoolQueueWords;
+    constexpr bool kRegen = RT_REGEN_MIN > 0 && VAR::FAMILY != FAMILY_C;
     Pool<NSLOT> pool;
     pool.w = smem + warp * kWarpWords;
     uint8_t* ready = reinterpret_cast<uint8_t*>(pool.w + F_COUNT * NSLOT);
     uint8_t* pend = ready + NSLOT;
-    volatile uint32_t* wq = pool.w + F_COUNT * NSLOT + 2 * (NSLOT / 4);   // the warp's chunk of the work queue
-    int n_ready = 0, n_pend = NSLOT;          // warp-uniform
-    if (lane < kPoolQueueWords) wq[lane] = 0u;
+    uint8_t* fresh = pend + NSLOT;            // kRegen: slots waiting for a new path (count in wq[WQ_NFRESH])
+    volatile uint32_t* wq = pool.w + F_COUNT * NSLOT + kPoolStacks * (NSLOT / 4);   // the warp's chunk of the work queue
+    int n_ready = 0, n_pend = kRegen ? 0 : NSLOT;          // warp-uniform
+    if (lane < kPoolQueueWords) wq[lane] = (kRegen && lane == WQ_NFRESH) ? (uint32_t)NSLOT : 0u;
 
     for (int s = lane; s < NSLOT; s += 32) {
         pool.seti(F_STATUS, s, ST_FETCH);
-        pend[s] = (uint8_t)s;
+        (kRegen ? fresh : pend)[s] = (uint8_t)s;
     }
     __syncwarp();
 
@@ -380,7 +412,9 @@ __device__ __forceinline__ void pool_body(const KParams& P)
         }
 
         // ---------------------------------------------------------------- resolve phase
-        if (active != kFull && n_pend > 0 && (n_pend >= P.resolve_min || active == 0u)) {
+        int n_wait = n_pend;          // slots the resolve phase could work on
+        if (kRegen && active != kFull) n_wait += (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
+        if (active != kFull && n_wait > 0 && (n_wait >= P.resolve_min || active == 0u)) {
             if (VAR::COUNT) c_rounds++;
             __syncwarp();    // the acquire above may have read the stack entries that parking overwrites
             if (my >= 0) {   // park: the slot stays ready-to-march
@@ -397,13 +431,35 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             __syncwarp();
             // One batch always; further batches only while they are full.  A small remainder stays on
             // the pending stack for the next round instead of costing a whole 32-wide pass.
-            do {
-                const int take = min(n_pend, 32);
-                const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
-                n_pend -= take;
-                if (VAR::COUNT) c_resolved += (unsigned long long)take;
-                resolve_batch<VAR, NSLOT>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt);
-            } while (n_pend >= 32);
+            if (!kRegen) {
+                do {
+                    const int take = min(n_pend, 32);
+                    const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
+                    n_pend -= take;
+                    if (VAR::COUNT) c_resolved += (unsigned long long)take;
+                    resolve_batch<VAR, NSLOT>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt);
+                } while (n_pend >= 32);
+            } else {
+                while (n_pend > 0) {
+                    const int take = min(n_pend, 32);
+                    const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
+                    n_pend -= take;
+                    if (VAR::COUNT) c_resolved += (unsigned long long)take;
+                    resolve_batch<VAR, NSLOT, MODE_HITS>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt, pend, &n_pend, fresh);
+                    if (n_pend < 32) break;
+                }
+                // regeneration: when enough slots wait for a new path, or when lanes would idle otherwise
+                for (;;) {
+                    const int n_fresh = (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
+                    if (n_fresh == 0 || !(n_fresh >= RT_REGEN_MIN || n_ready < 32)) break;
+                    const int take = min(n_fresh, 32);
+                    const int slot = lane < take ? (int)fresh[n_fresh - 1 - lane] : -1;
+                    __syncwarp();
+                    if (lane == 0) wq[WQ_NFRESH] = (uint32_t)(n_fresh - take);
+                    __syncwarp();
+                    resolve_batch<VAR, NSLOT, MODE_FRESH>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt, pend, &n_pend, fresh);
+                }
+            }
             continue;
         }
         if (active == 0u) break;   // nothing marching, nothing pending, nothing ready: pool drained

@@ -74,6 +74,7 @@ def test_scratch_chunking_is_invisible(monkeypatch):
     {"RTPBR_JIT_PAIRS": "1"}, {"RTPBR_JIT_PAIRS": "0"}, {"RTPBR_PACK_CLAMPS": "4"}, {"RTPBR_ALU_CLAMPS": "2"},
     {"RTPBR_MARCH_UNROLL": "2", "RTPBR_SPHERE_PAIRS": "0"}, {"RTPBR_POOL_SLOTS": "32", "RTPBR_RESOLVE_MIN": "1"}, {"RTPBR_POOL_SLOTS": "96", "RTPBR_POOL_BLOCK": "128"},
     {"RTPBR_PACK_CLAMPS": "2", "RTPBR_ALU_CLAMPS": "1", "RTPBR_MARCH_UNROLL": "2", "RTPBR_POOL_MIN_BLOCKS": "3"},
+    {"RTPBR_REGEN_MIN": "16"}, {"RTPBR_REGEN_MIN": "1", "RTPBR_POOL_SLOTS": "32"},
 ], ids=lambda k: ",".join(f"{a[6:]}={b}" for a, b in k.items()))
 def test_tuning_knobs_do_not_change_a_bit(monkeypatch, knobs):
     # code-shape and pool-geometry knobs of the specialised kernel
