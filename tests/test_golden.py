@@ -82,6 +82,49 @@ def test_product_host_code_matches_reference_source(path):
     assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, S), g["image_buffer"])
 
 
+# ---------------------------------------------------------------- BASELINE.json configs[0] at its real size
+C0 = os.path.join(GOLDEN, "c0_columns.npz")
+
+
+def c0_fixture():
+    """32 spread columns of the 256 x 256 x 1 spp x 4 bounce image, rendered by the reference's own
+    cornell_box_shortest.py under the stand-in (tests/tools/gen_golden.py c0_columns)."""
+    g = np.load(C0)
+    W, H, B, S, seed = params(g)
+    assert (W, H, B, S) == (256, 256, 4, 1)                       # exactly the configuration BASELINE.json names
+    return g, W, H, B, seed, g["columns"].astype(int), g["image_buffer_columns"]
+
+
+def test_oracle_matches_reference_source_on_configs0_at_full_size():
+    g, W, H, B, seed, cols, want = c0_fixture()
+    cfg = po.cornell_shortest_config(W, H, B, seed)
+    objs = po.objects_array(po.cornell_shortest_objects())
+    got = po.pathtrace(cfg, objs, 1)
+    assert want.shape == (len(cols), H, 4) and (want[..., 3] == 1.0).all()
+    assert len(np.unique(want[..., :3])) > 10 and (want[..., :3].sum(-1) > 0).mean() > 0.2      # a real image, not zeros
+    assert np.array_equal(got[cols], want)
+
+
+def test_product_host_code_matches_reference_source_on_configs0_at_full_size():
+    from raytracingpbr_b200 import scenes
+    g, W, H, B, seed, cols, want = c0_fixture()
+    cfg, objs, cam, _ = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=seed)
+    assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, 1)[cols], want)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_source_on_configs0_at_full_size():
+    from raytracingpbr_b200 import PathTracer, _native as N, scenes
+    g, W, H, B, seed, cols, want = c0_fixture()
+    for kernel in (N.KERNEL_PERSISTENT, N.KERNEL_SIMPLE):
+        cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=seed, kernel=kernel)
+        with PathTracer(cfg, objs, cam, tm) as pt:
+            pt.refresh()
+            pt.pathtrace(1)
+            buf = pt.image_buffer.to_numpy()
+        assert np.array_equal(buf[cols], want), kernel
+
+
 FAMILY_B = ["cornell_box", "cornell_v2", "cornell_v3", "tokyo_ibl", "scene_demo", "bunny_glass"]
 
 

@@ -141,6 +141,40 @@ def gen_shortest(name, width, height, bounces, spp, seed):
 
 
 # ------------------------------------------------------------------------------ families B / C
+def _c0_worker(job):
+    name, width, height, bounces, seed, cols = job
+    subs = [("image_resolution = (512, 512)", f"image_resolution = ({width}, {height})"),
+            ("for i in range(3):", f"for i in range({bounces}):")]
+    m = load_script("examples/cornell_box/cornell_box_shortest.py", f"ref_shortest_{name}_{cols[0]}", subs)
+    install_rng(seed)
+    want = set(cols)
+    ti.pixel_filter = lambda i, j: i in want
+    ti.rng.launch = 0
+    m.render(vec3(0, 0, 3.5), vec3(0, 0, -1), vec3(0, 1, 0))              # the call in main(), shortest:135
+    ti.pixel_filter = None
+    buf = m.image_buffer.to_numpy()
+    return cols, buf[cols]
+
+
+def gen_c0_columns(name, width, height, bounces, seed, columns, workers=8):
+    """BASELINE.json configs[0] itself -- cornell_box_shortest.py, 256 x 256, 1 spp, 4 bounces -- at FULL resolution,
+    for a spread subset of image columns (the scalar stand-in needs ~0.3 s per sample; pixels are independent and
+    the RNG stream is keyed by the global pixel index, so a column subset of the full image is exact)."""
+    import multiprocessing as mp
+    t0 = time.time()
+    columns = sorted(columns)
+    jobs = [(name, width, height, bounces, seed, columns[k::workers]) for k in range(workers) if columns[k::workers]]
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        parts = pool.map(_c0_worker, jobs)
+    img = np.zeros((len(columns), height, 4), np.float32)
+    for cols, data in parts:
+        for c, d in zip(cols, data):
+            img[columns.index(c)] = d
+    print(f"  {name}: {len(columns)} columns of {width}x{height} in {time.time() - t0:.1f} s")
+    return {"width": width, "height": height, "bounces": bounces, "spp": 1, "seed": seed,
+            "columns": np.asarray(columns, np.int32), "image_buffer_columns": img}
+
+
 def synthetic_env(w=16, h=8, seed=3):
     """Stand-in for ti.tools.imread(<.hdr>): uint8 (W, H, 3) like stb's LDR conversion returns
     (SURVEY.md 8(c)); small and seeded so the fixture stays tiny."""
@@ -449,6 +483,10 @@ FIXTURES = {
     # name: (generator, kwargs)
     "shortest_3b": (gen_shortest, dict(width=12, height=10, bounces=3, spp=2, seed=0)),      # the file as shipped (3 bounces)
     "shortest_8b": (gen_shortest, dict(width=10, height=8, bounces=8, spp=2, seed=7)),       # BASELINE configs[1] bounce count
+    # BASELINE.json configs[0] at its real size: 32 spread columns of the 256 x 256 x 1 spp x 4 bounce image
+    "c0_columns": (gen_c0_columns, dict(width=256, height=256, bounces=4, seed=0,
+                                        columns=[0, 1, 7, 15, 31, 40, 63, 64, 77, 90, 100, 111, 120, 127, 128, 129, 140, 150, 160, 170,
+                                                 180, 191, 192, 200, 210, 220, 230, 240, 250, 253, 254, 255])),
     "cornell_box": (gen_cornell_box, dict(width=8, height=8, bounces=6, spp=2, seed=1)),
     "cornell_v2": (gen_cornell_box, dict(width=8, height=8, bounces=3, spp=2, seed=9, v2=True)),
     "cornell_v3": (gen_cornell_v3, dict(width=8, height=8, bounces=3, spp=2, seed=2)),

@@ -45,6 +45,7 @@ class _Rng:
 
 
 rng = _Rng()
+pixel_filter = None     # optional callable (i, j) -> bool restricting 2-D struct-for loops (see _Field.__iter__)
 
 
 def random(dtype=float):
@@ -201,6 +202,8 @@ class _Field:
             return
         for key in _it.product(*[range(s) for s in self.shape]):
             if len(self.shape) == 2:
+                if pixel_filter is not None and not pixel_filter(key[0], key[1]):
+                    continue       # gen_golden.py renders a subset of the pixels of a large image (pixels are independent)
                 rng.pixel = key[0] * self.shape[1] + key[1]
                 rng.n = 0
             yield key
