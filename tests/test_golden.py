@@ -82,47 +82,72 @@ def test_product_host_code_matches_reference_source(path):
     assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, S), g["image_buffer"])
 
 
-# ---------------------------------------------------------------- BASELINE.json configs[0] at its real size
-C0 = os.path.join(GOLDEN, "c0_columns.npz")
+# ---------------------------------------------------------------- BASELINE.json configurations at their real size
+# Spread columns of launch 0 (1 spp) of the full-resolution images, rendered by the reference's own source files under
+# the stand-in (tests/tools/gen_golden.py *_columns): configs[0] 256^2 / 4 bounces, configs[1] 1024^2 / 8 bounces,
+# configs[4] 4096^2 / 8 bounces (cornell_box_shortest.py), configs[3] 1920 x 1080 / 8 bounces (tokyo_ibl.py) and
+# configs[2] 1024^2 / 16 bounces, frame 0 (bunny_sdf_glass.py).
+REAL_SIZE = {"c0_columns": (256, 256, 4), "c1_columns": (1024, 1024, 8), "c4_columns": (4096, 4096, 8), "c3_columns": (1920, 1080, 8),
+             "c2_columns": (1024, 1024, 16)}
+REAL_SIZE_PRESENT = [n for n in REAL_SIZE if os.path.exists(os.path.join(GOLDEN, n + ".npz"))]
 
 
-def c0_fixture():
-    """32 spread columns of the 256 x 256 x 1 spp x 4 bounce image, rendered by the reference's own
-    cornell_box_shortest.py under the stand-in (tests/tools/gen_golden.py c0_columns)."""
-    g = np.load(C0)
+def real_size_case(name):
+    from raytracingpbr_b200 import scenes
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
     W, H, B, S, seed = params(g)
-    assert (W, H, B, S) == (256, 256, 4, 1)                       # exactly the configuration BASELINE.json names
-    return g, W, H, B, seed, g["columns"].astype(int), g["image_buffer_columns"]
-
-
-def test_oracle_matches_reference_source_on_configs0_at_full_size():
-    g, W, H, B, seed, cols, want = c0_fixture()
-    cfg = po.cornell_shortest_config(W, H, B, seed)
-    objs = po.objects_array(po.cornell_shortest_objects())
-    got = po.pathtrace(cfg, objs, 1)
+    assert (W, H, B) == REAL_SIZE[name] and S == 1              # exactly the configuration BASELINE.json names
+    cols, want = g["columns"].astype(int), g["image_buffer_columns"]
     assert want.shape == (len(cols), H, 4) and (want[..., 3] == 1.0).all()
     assert len(np.unique(want[..., :3])) > 10 and (want[..., :3].sum(-1) > 0).mean() > 0.2      # a real image, not zeros
-    assert np.array_equal(got[cols], want)
+    env = None
+    if name == "c3_columns":
+        cfg, objs, cam, tm = scenes.tokyo_ibl(W, H, max_bounces=B, seed=seed)
+        cam.lookfrom, cam.lookat = g["lookfrom"], g["lookat"]
+        env = common.env_table(g["env_u8"], 1.8, 2.2)               # tokyo_ibl.py:60
+    elif name == "c2_columns":
+        cfg, objs, cam, tm = scenes.bunny_glass(W, H, max_bounces=B, seed=seed, frame=int(g["frame"]))
+        cam.lookfrom, cam.lookat = g["lookfrom"], g["lookat"]
+        env = common.env_table(g["env_u8"], 1.8, 2.2)               # bunny_sdf_glass.py:279-280
+    else:
+        cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=seed)
+    return cfg, objs, cam, tm, env, cols, want
 
 
-def test_product_host_code_matches_reference_source_on_configs0_at_full_size():
-    from raytracingpbr_b200 import scenes
-    g, W, H, B, seed, cols, want = c0_fixture()
-    cfg, objs, cam, _ = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=seed)
-    assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, 1)[cols], want)
+def test_configs0_fixture_present():
+    assert "c0_columns" in REAL_SIZE_PRESENT
+
+
+@pytest.mark.parametrize("name", REAL_SIZE_PRESENT)
+def test_oracle_matches_reference_source_at_real_size(name):
+    cfg, objs, cam, tm, env, cols, want = real_size_case(name)
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    buf = np.zeros((cfg.width, cfg.height, 4), np.float32)
+    for c0 in cols:                                             # the oracle renders single columns of the full image
+        po.pathtrace(oc, oo, 1, env=env, i0=int(c0), i1=int(c0) + 1, image_buffer=buf)
+    assert np.array_equal(buf[cols], want), name
+
+
+@pytest.mark.parametrize("name", [n for n in REAL_SIZE_PRESENT if n not in ("c4_columns", "c2_columns")])   # (whole images: keep the CPU suite short)
+def test_product_host_code_matches_reference_source_at_real_size(name):
+    cfg, objs, cam, tm, env, cols, want = real_size_case(name)
+    assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, 1, env=env)[cols], want)
 
 
 @pytest.mark.gpu
-def test_cuda_matches_reference_source_on_configs0_at_full_size():
-    from raytracingpbr_b200 import PathTracer, _native as N, scenes
-    g, W, H, B, seed, cols, want = c0_fixture()
+@pytest.mark.parametrize("name", REAL_SIZE_PRESENT)
+def test_cuda_matches_reference_source_at_real_size(name):
+    from raytracingpbr_b200 import PathTracer, _native as N
+    cfg, objs, cam, tm, env, cols, want = real_size_case(name)
     for kernel in (N.KERNEL_PERSISTENT, N.KERNEL_SIMPLE):
-        cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=seed, kernel=kernel)
+        cfg.kernel = kernel
         with PathTracer(cfg, objs, cam, tm) as pt:
+            if env is not None:
+                pt.set_envmap(env)
             pt.refresh()
             pt.pathtrace(1)
             buf = pt.image_buffer.to_numpy()
-        assert np.array_equal(buf[cols], want), kernel
+        assert np.array_equal(buf[cols], want), (name, kernel)
 
 
 FAMILY_B = ["cornell_box", "cornell_v2", "cornell_v3", "tokyo_ibl", "scene_demo", "bunny_glass"]

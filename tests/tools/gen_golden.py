@@ -141,38 +141,66 @@ def gen_shortest(name, width, height, bounces, spp, seed):
 
 
 # ------------------------------------------------------------------------------ families B / C
-def _c0_worker(job):
-    name, width, height, bounces, seed, cols = job
-    subs = [("image_resolution = (512, 512)", f"image_resolution = ({width}, {height})"),
-            ("for i in range(3):", f"for i in range({bounces}):")]
-    m = load_script("examples/cornell_box/cornell_box_shortest.py", f"ref_shortest_{name}_{cols[0]}", subs)
-    install_rng(seed)
+def _columns_worker(job):
+    kind, name, width, height, bounces, seed, cols = job
     want = set(cols)
+    install_rng(seed)
+    if kind == "shortest":
+        subs = [("image_resolution = (512, 512)", f"image_resolution = ({width}, {height})"),
+                ("for i in range(3):", f"for i in range({bounces}):")]
+        m = load_script("examples/cornell_box/cornell_box_shortest.py", f"ref_shortest_{name}_{cols[0]}", subs)
+        run = lambda: m.render(vec3(0, 0, 3.5), vec3(0, 0, -1), vec3(0, 1, 0))          # the call in main(), shortest:135
+    elif kind == "tokyo":
+        env_u8 = synthetic_env()
+        ti.tools.imread = lambda path: env_u8
+        subs = [("image_resolution = (192*15, 108*15)", f"image_resolution = ({width}, {height})"),
+                ("MAX_RAYTRACE = 512", f"MAX_RAYTRACE = {bounces}")]
+        m = load_script("examples/scene_demo/tokyo_ibl.py", f"ref_tokyo_{name}_{cols[0]}", subs)
+        m.init_scene()
+        run = lambda: m.sample(vec3(0, -0.2, 4), vec3(0, -0.2, 3), vec3(0, 1, 0))
+    elif kind == "bunny":
+        env_u8 = synthetic_env(seed=5)
+        ti.tools.imread = lambda path: env_u8
+        subs = [("image_resolution = (1920, 1080)", f"image_resolution = ({width}, {height})"),
+                ("MAX_RAYTRACE = 512", f"MAX_RAYTRACE = {bounces}"),
+                ("while True:", "while False:")]
+        m = load_script("examples/bunny/bunny_sdf_glass.py", f"ref_bunny_{name}_{cols[0]}", subs)
+        run = lambda: m.sample(vec3(0, 0, 4), vec3(0, 0, 3), vec3(0, 1, 0), 0)            # frame 0
+    else:
+        raise KeyError(kind)
     ti.pixel_filter = lambda i, j: i in want
     ti.rng.launch = 0
-    m.render(vec3(0, 0, 3.5), vec3(0, 0, -1), vec3(0, 1, 0))              # the call in main(), shortest:135
+    run()
     ti.pixel_filter = None
     buf = m.image_buffer.to_numpy()
     return cols, buf[cols]
 
 
-def gen_c0_columns(name, width, height, bounces, seed, columns, workers=8):
-    """BASELINE.json configs[0] itself -- cornell_box_shortest.py, 256 x 256, 1 spp, 4 bounces -- at FULL resolution,
-    for a spread subset of image columns (the scalar stand-in needs ~0.3 s per sample; pixels are independent and
-    the RNG stream is keyed by the global pixel index, so a column subset of the full image is exact)."""
+def gen_columns(name, kind, width, height, bounces, seed, columns, workers=8):
+    """A BASELINE.json configuration at its REAL resolution and bounce count, launch 0 (1 spp), for a spread subset of
+    image columns: the scalar stand-in needs ~0.3 s per sample, pixels are independent and the RNG stream is keyed by
+    the global pixel index, so a column subset of the full image is exact."""
     import multiprocessing as mp
     t0 = time.time()
     columns = sorted(columns)
-    jobs = [(name, width, height, bounces, seed, columns[k::workers]) for k in range(workers) if columns[k::workers]]
+    jobs = [(kind, name, width, height, bounces, seed, columns[k::workers]) for k in range(workers) if columns[k::workers]]
     with mp.get_context("fork").Pool(len(jobs)) as pool:
-        parts = pool.map(_c0_worker, jobs)
+        parts = pool.map(_columns_worker, jobs)
     img = np.zeros((len(columns), height, 4), np.float32)
     for cols, data in parts:
         for c, d in zip(cols, data):
             img[columns.index(c)] = d
     print(f"  {name}: {len(columns)} columns of {width}x{height} in {time.time() - t0:.1f} s")
-    return {"width": width, "height": height, "bounces": bounces, "spp": 1, "seed": seed,
-            "columns": np.asarray(columns, np.int32), "image_buffer_columns": img}
+    out = {"width": width, "height": height, "bounces": bounces, "spp": 1, "seed": seed,
+           "columns": np.asarray(columns, np.int32), "image_buffer_columns": img}
+    if kind == "tokyo":
+        out["env_u8"] = synthetic_env()
+        out["lookfrom"], out["lookat"] = np.array([0, -0.2, 4], np.float32), np.array([0, -0.2, 3], np.float32)
+    if kind == "bunny":
+        out["env_u8"] = synthetic_env(seed=5)
+        out["frame"] = 0
+        out["lookfrom"], out["lookat"] = np.array([0, 0, 4], np.float32), np.array([0, 0, 3], np.float32)
+    return out
 
 
 def synthetic_env(w=16, h=8, seed=3):
@@ -484,9 +512,18 @@ FIXTURES = {
     "shortest_3b": (gen_shortest, dict(width=12, height=10, bounces=3, spp=2, seed=0)),      # the file as shipped (3 bounces)
     "shortest_8b": (gen_shortest, dict(width=10, height=8, bounces=8, spp=2, seed=7)),       # BASELINE configs[1] bounce count
     # BASELINE.json configs[0] at its real size: 32 spread columns of the 256 x 256 x 1 spp x 4 bounce image
-    "c0_columns": (gen_c0_columns, dict(width=256, height=256, bounces=4, seed=0,
-                                        columns=[0, 1, 7, 15, 31, 40, 63, 64, 77, 90, 100, 111, 120, 127, 128, 129, 140, 150, 160, 170,
-                                                 180, 191, 192, 200, 210, 220, 230, 240, 250, 253, 254, 255])),
+    "c0_columns": (gen_columns, dict(kind="shortest", width=256, height=256, bounces=4, seed=0,
+                                     columns=[0, 1, 7, 15, 31, 40, 63, 64, 77, 90, 100, 111, 120, 127, 128, 129, 140, 150, 160, 170,
+                                              180, 191, 192, 200, 210, 220, 230, 240, 250, 253, 254, 255])),
+    # configs[1] / configs[4]: the same scene at 1024^2 and 4096^2 with 8 bounces; configs[3]: tokyo_ibl at 1920 x 1080, 8 bounces
+    "c1_columns": (gen_columns, dict(kind="shortest", width=1024, height=1024, bounces=8, seed=0,
+                                     columns=[0, 255, 400, 511, 512, 640, 900, 1023])),
+    "c4_columns": (gen_columns, dict(kind="shortest", width=4096, height=4096, bounces=8, seed=0, columns=[1500, 2047])),
+    # configs[2]: bunny_sdf_glass.py at 1024 x 1024, 16 bounces, frame 0 (the neural SDF costs seconds per sample here)
+    "c2_columns": (gen_columns, dict(kind="bunny", width=1024, height=1024, bounces=16, seed=0,
+                                     columns=[300, 420, 480, 511, 512, 560, 640, 760])),
+    "c3_columns": (gen_columns, dict(kind="tokyo", width=1920, height=1080, bounces=8, seed=0,
+                                     columns=[0, 480, 800, 959, 960, 1100, 1500, 1919])),
     "cornell_box": (gen_cornell_box, dict(width=8, height=8, bounces=6, spp=2, seed=1)),
     "cornell_v2": (gen_cornell_box, dict(width=8, height=8, bounces=3, spp=2, seed=9, v2=True)),
     "cornell_v3": (gen_cornell_v3, dict(width=8, height=8, bounces=3, spp=2, seed=2)),
