@@ -150,6 +150,53 @@ def test_cuda_matches_reference_source_at_real_size(name):
         assert np.array_equal(buf[cols], want), (name, kernel)
 
 
+SRC_COLUMNS = os.path.join(GOLDEN, "src_columns.npz")
+
+
+def src_columns_case():
+    """The src/ package (family C) at its shipped 768 x 432, 16 launches of pathtrace(), 8 spread columns."""
+    from raytracingpbr_b200 import scenes
+    g = np.load(SRC_COLUMNS)
+    W, H, seed, launches = int(g["width"]), int(g["height"]), int(g["seed"]), int(g["launches"])
+    assert (W, H) == (768, 432)                                     # src/config.py:7
+    cfg, objs, cam, tm = scenes.src_scene(W, H, seed=seed)
+    cam.lookfrom, cam.lookat = g["lookfrom"], g["lookat"]
+    env = common.env_table(g["env_u8"], 1.4, 2.2)                   # src/ibl.py:33
+    cols = g["columns"].astype(int)
+    assert g["image_buffer_columns"][..., 3].sum() > 0 and (g["ray_buffer_columns"][..., 9].view(np.int32) < 0).any()
+    return cfg, objs, cam, tm, env, launches, cols, g["image_buffer_columns"], g["ray_buffer_columns"]
+
+
+@pytest.mark.skipif(not os.path.exists(SRC_COLUMNS), reason="fixture not generated")
+def test_oracle_family_c_matches_reference_source_at_real_size():
+    cfg, objs, cam, tm, env, launches, cols, want_img, want_rb = src_columns_case()
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    img = np.zeros((cfg.width, cfg.height, 4), np.float32)
+    rb = np.zeros((cfg.width, cfg.height, 10), np.float32)
+    for c0 in cols:
+        po.pathtrace(oc, oo, launches, env=env, ray_buffer=rb, image_buffer=img, i0=int(c0), i1=int(c0) + 1)
+    assert np.array_equal(img[cols], want_img)
+    assert np.array_equal(rb[cols].view(np.int32), want_rb.view(np.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SRC_COLUMNS), reason="fixture not generated")
+def test_cuda_family_c_matches_reference_source_at_real_size():
+    from raytracingpbr_b200 import PathTracer, _native as N
+    cfg, objs, cam, tm, env, launches, cols, want_img, want_rb = src_columns_case()
+    for kernel in (N.KERNEL_PERSISTENT, N.KERNEL_SIMPLE):
+        cfg.kernel = kernel
+        with PathTracer(cfg, objs, cam, tm) as pt:
+            pt.set_envmap(env)
+            pt.refresh()
+            pt.pathtrace(5)                                         # 16 reference launches in two kernel launches
+            pt.pathtrace(launches - 5)
+            img = pt.image_buffer.to_numpy()
+            rb = pt.ray_buffer.to_numpy()
+        assert np.array_equal(img[cols], want_img), kernel
+        assert np.array_equal(rb[cols].view(np.int32), want_rb.view(np.int32)), kernel
+
+
 FAMILY_B = ["cornell_box", "cornell_v2", "cornell_v3", "tokyo_ibl", "scene_demo", "bunny_glass"]
 
 

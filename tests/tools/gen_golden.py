@@ -507,6 +507,64 @@ def gen_src(name, width, height, launches, seed, spp_per_launch=1, adaptive=Fals
     return out
 
 
+def _src_columns_worker(job):
+    name, width, height, launches, seed, cols = job
+    env_u8 = synthetic_env(seed=9)
+    ti.tools.imread = lambda path: env_u8
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    subs = {"src.config": [("image_resolution = (1920 * 4 // 10, 1080 * 4 // 10)", f"image_resolution = ({width}, {height})")]}
+    finder = _SrcFinder(subs)
+    sys.meta_path.insert(0, finder)
+    try:
+        import src.renderer as rend
+        import src.pathtracer as pt
+        import src.scene as sc
+        import src.camera as cam
+        import src.fileds as fld
+        import src.pbr  # noqa: F401
+    finally:
+        sys.meta_path.remove(finder)
+    cam.smooth.position[None] = vec3(0, -0.2, 4.0)             # src/main.py:17 camera.position(0, -0.2, 4.0)
+    cam.smooth.lookat[None] = vec3(0, -0.2, 3.0)
+    cam.smooth.up[None] = vec3(0, 1, 0)
+    sc.build_scene()
+    install_rng(seed)
+    want = set(cols)
+    ti.pixel_filter = lambda i, j: i in want
+    rend.refresh()
+    for L in range(launches):
+        ti.rng.launch = L
+        pt.pathtrace()
+    ti.pixel_filter = None
+    rb = np.zeros((width, height, 10), np.float32)
+    rb[..., 0:3] = fld.ray_buffer.member("origin")
+    rb[..., 3:6] = fld.ray_buffer.member("direction")
+    rb[..., 6:9] = fld.ray_buffer.member("color")
+    rb[..., 9] = fld.ray_buffer.member("depth").astype(np.int32).view(np.float32)
+    return cols, fld.image_buffer.to_numpy()[cols], rb[cols]
+
+
+def gen_src_columns(name, width, height, launches, seed, columns, workers=8):
+    """The src/ package (family C) at the resolution src/config.py ships (768 x 432): `launches` launches of kernel
+    pathtrace() (one bounce per pixel per launch, state carried in ray_buffer) for a spread subset of image columns."""
+    import multiprocessing as mp
+    t0 = time.time()
+    columns = sorted(columns)
+    jobs = [(name, width, height, launches, seed, columns[k::workers]) for k in range(workers) if columns[k::workers]]
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        parts = pool.map(_src_columns_worker, jobs)
+    img = np.zeros((len(columns), height, 4), np.float32)
+    rb = np.zeros((len(columns), height, 10), np.float32)
+    for cols, a, b in parts:
+        for c, x, y in zip(cols, a, b):
+            img[columns.index(c)], rb[columns.index(c)] = x, y
+    print(f"  {name}: {len(columns)} columns of {width}x{height} x {launches} launches in {time.time() - t0:.1f} s")
+    return {"width": width, "height": height, "launches": launches, "seed": seed, "env_u8": synthetic_env(seed=9), "spp_per_launch": 1,
+            "lookfrom": np.array([0, -0.2, 4], np.float32), "lookat": np.array([0, -0.2, 3], np.float32),
+            "columns": np.asarray(columns, np.int32), "image_buffer_columns": img, "ray_buffer_columns": rb}
+
+
 FIXTURES = {
     # name: (generator, kwargs)
     "shortest_3b": (gen_shortest, dict(width=12, height=10, bounces=3, spp=2, seed=0)),      # the file as shipped (3 bounces)
@@ -524,6 +582,8 @@ FIXTURES = {
                                      columns=[300, 420, 480, 511, 512, 560, 640, 760])),
     "c3_columns": (gen_columns, dict(kind="tokyo", width=1920, height=1080, bounces=8, seed=0,
                                      columns=[0, 480, 800, 959, 960, 1100, 1500, 1919])),
+    # the src/ package at its shipped resolution, 16 launches of pathtrace()
+    "src_columns": (gen_src_columns, dict(width=768, height=432, launches=16, seed=0, columns=[0, 100, 250, 383, 384, 500, 640, 767])),
     "cornell_box": (gen_cornell_box, dict(width=8, height=8, bounces=6, spp=2, seed=1)),
     "cornell_v2": (gen_cornell_box, dict(width=8, height=8, bounces=3, spp=2, seed=9, v2=True)),
     "cornell_v3": (gen_cornell_v3, dict(width=8, height=8, bounces=3, spp=2, seed=2)),
