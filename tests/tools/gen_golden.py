@@ -158,6 +158,23 @@ def _columns_worker(job):
         m = load_script("examples/scene_demo/tokyo_ibl.py", f"ref_tokyo_{name}_{cols[0]}", subs)
         m.init_scene()
         run = lambda: m.sample(vec3(0, -0.2, 4), vec3(0, -0.2, 3), vec3(0, 1, 0))
+    elif kind == "cornell_box":
+        subs = [("image_resolution = (1920 // 4, 1920 // 4)", f"image_resolution = ({width}, {height})"),
+                ("MAX_RAYTRACE = 128", f"MAX_RAYTRACE = {bounces}")]
+        m = load_script("examples/cornell_box/cornell_box.py", f"ref_cornell_box_{name}_{cols[0]}", subs)
+        run = lambda: m.render(vec3(0, 0, 3), vec3(0, 0, -1), vec3(0, 1, 0), False)
+    elif kind == "cornell_v2":
+        subs = [("image_resolution = (512, 512)", f"image_resolution = ({width}, {height})"),
+                ("MAX_RAYTRACE = 3", f"MAX_RAYTRACE = {bounces}")]
+        m = load_script("examples/cornell_box/cornell_box_v2.py", f"ref_cornell_v2_{name}_{cols[0]}", subs)
+        run = lambda: m.render(vec3(0, 0, 35), vec3(0, 0, -10), vec3(0, 1, 0), False)
+    elif kind == "scene_demo":
+        env_u8 = synthetic_env()
+        ti.tools.imread = lambda path: env_u8
+        subs = [("image_resolution = (1920 // 4, 1080 // 4)", f"image_resolution = ({width}, {height})")]
+        m = load_script("examples/scene_demo/main.py", f"ref_scene_demo_{name}_{cols[0]}", subs)
+        m.init_scene()
+        run = lambda: m.sample(vec3(0, -0.2, 4), vec3(0, -0.2, 3), vec3(0, 1, 0))
     elif kind == "bunny":
         env_u8 = synthetic_env(seed=5)
         ti.tools.imread = lambda path: env_u8
@@ -194,6 +211,13 @@ def gen_columns(name, kind, width, height, bounces, seed, columns, workers=8):
     out = {"width": width, "height": height, "bounces": bounces, "spp": 1, "seed": seed,
            "columns": np.asarray(columns, np.int32), "image_buffer_columns": img}
     if kind == "tokyo":
+        out["env_u8"] = synthetic_env()
+        out["lookfrom"], out["lookat"] = np.array([0, -0.2, 4], np.float32), np.array([0, -0.2, 3], np.float32)
+    if kind == "cornell_box":
+        out["lookfrom"], out["lookat"] = np.array([0, 0, 3], np.float32), np.array([0, 0, -1], np.float32)
+    if kind == "cornell_v2":
+        out["lookfrom"], out["lookat"] = np.array([0, 0, 35], np.float32), np.array([0, 0, -10], np.float32)
+    if kind == "scene_demo":
         out["env_u8"] = synthetic_env()
         out["lookfrom"], out["lookat"] = np.array([0, -0.2, 4], np.float32), np.array([0, -0.2, 3], np.float32)
     if kind == "bunny":
@@ -582,6 +606,10 @@ FIXTURES = {
                                      columns=[300, 420, 480, 511, 512, 560, 640, 760])),
     "c3_columns": (gen_columns, dict(kind="tokyo", width=1920, height=1080, bounces=8, seed=0,
                                      columns=[0, 480, 800, 959, 960, 1100, 1500, 1919])),
+    # the other example scripts exactly as shipped (resolution and bounce cap of the files)
+    "cornell_box_columns": (gen_columns, dict(kind="cornell_box", width=480, height=480, bounces=128, seed=0, columns=[0, 120, 239, 240, 300, 479])),
+    "cornell_v2_columns": (gen_columns, dict(kind="cornell_v2", width=512, height=512, bounces=3, seed=0, columns=[0, 100, 255, 256, 300, 400, 450, 511])),
+    "scene_demo_columns": (gen_columns, dict(kind="scene_demo", width=480, height=270, bounces=128, seed=0, columns=[0, 100, 200, 239, 240, 300, 400, 479])),
     # the src/ package at its shipped resolution, 16 launches of pathtrace()
     "src_columns": (gen_src_columns, dict(width=768, height=432, launches=16, seed=0, columns=[0, 100, 250, 383, 384, 500, 640, 767])),
     "cornell_box": (gen_cornell_box, dict(width=8, height=8, bounces=6, spp=2, seed=1)),
