@@ -101,7 +101,7 @@ def real_size_case(name):
     assert (W, H, B) == REAL_SIZE[name] and S == 1              # exactly the configuration BASELINE.json names
     cols, want = g["columns"].astype(int), g["image_buffer_columns"]
     assert want.shape == (len(cols), H, 4) and (want[..., 3] == 1.0).all()
-    assert len(np.unique(want[..., :3])) > 10 and (want[..., :3].sum(-1) > 0).mean() > 0.2      # a real image, not zeros
+    assert len(np.unique(want[..., :3])) > 10 and (want[..., :3].sum(-1) > 0).mean() > 0.05     # a real image, not zeros
     env = None
     if name == "c3_columns":
         cfg, objs, cam, tm = scenes.tokyo_ibl(W, H, max_bounces=B, seed=seed)
