@@ -90,7 +90,8 @@ def test_product_host_code_matches_reference_source(path):
 REAL_SIZE = {"c0_columns": (256, 256, 4), "c1_columns": (1024, 1024, 8), "c4_columns": (4096, 4096, 8), "c3_columns": (1920, 1080, 8),
              "c2_columns": (1024, 1024, 16),
              # the remaining example scripts exactly as shipped (resolution and bounce cap of the files)
-             "cornell_box_columns": (480, 480, 128), "cornell_v2_columns": (512, 512, 3), "scene_demo_columns": (480, 270, 128)}
+             "cornell_box_columns": (480, 480, 128), "cornell_v2_columns": (512, 512, 3), "cornell_v3_columns": (512, 512, 3),
+             "scene_demo_columns": (480, 270, 128)}
 REAL_SIZE_PRESENT = [n for n in REAL_SIZE if os.path.exists(os.path.join(GOLDEN, n + ".npz"))]
 
 
@@ -107,9 +108,9 @@ def real_size_case(name):
         cfg, objs, cam, tm = scenes.tokyo_ibl(W, H, max_bounces=B, seed=seed)
         cam.lookfrom, cam.lookat = g["lookfrom"], g["lookat"]
         env = common.env_table(g["env_u8"], 1.8, 2.2)               # tokyo_ibl.py:60
-    elif name in ("cornell_box_columns", "cornell_v2_columns", "scene_demo_columns"):
+    elif name in ("cornell_box_columns", "cornell_v2_columns", "cornell_v3_columns", "scene_demo_columns"):
         preset = {"cornell_box_columns": scenes.cornell_box, "cornell_v2_columns": scenes.cornell_box_v2,
-                  "scene_demo_columns": scenes.scene_demo}[name]
+                  "cornell_v3_columns": scenes.cornell_box_v3, "scene_demo_columns": scenes.scene_demo}[name]
         cfg, objs, cam, tm = preset(W, H, max_bounces=B, seed=seed)
         cam.lookfrom, cam.lookat = g["lookfrom"], g["lookat"]
     elif name == "c2_columns":

@@ -168,6 +168,19 @@ def _columns_worker(job):
                 ("MAX_RAYTRACE = 3", f"MAX_RAYTRACE = {bounces}")]
         m = load_script("examples/cornell_box/cornell_box_v2.py", f"ref_cornell_v2_{name}_{cols[0]}", subs)
         run = lambda: m.render(vec3(0, 0, 35), vec3(0, 0, -10), vec3(0, 1, 0), False)
+    elif kind == "cornell_v3":
+        d = "examples/cornell_box/cornell_box_v3"
+        for n in ["config", "dataclass", "util", "scene", "sdf", "pbr", "pathtracer", "postprocessor", "renderer"]:
+            sys.modules.pop(n, None)
+        load_script(f"{d}/config.py", "config", [("image_resolution = (512, 512)", f"image_resolution = ({width}, {height})"),
+                                                 ("MAX_RAYTRACE = 3", f"MAX_RAYTRACE = {bounces}")])
+        sys.path.insert(0, os.path.join(REF, d))
+        try:
+            import renderer as rmod
+            import scene as m          # image_buffer lives in scene.py
+        finally:
+            sys.path.pop(0)
+        run = lambda: rmod.render(vec3(0, 0, 35), vec3(0, 0, -10), vec3(0, 1, 0), False)
     elif kind == "scene_demo":
         env_u8 = synthetic_env()
         ti.tools.imread = lambda path: env_u8
@@ -215,6 +228,8 @@ def gen_columns(name, kind, width, height, bounces, seed, columns, workers=8):
         out["lookfrom"], out["lookat"] = np.array([0, -0.2, 4], np.float32), np.array([0, -0.2, 3], np.float32)
     if kind == "cornell_box":
         out["lookfrom"], out["lookat"] = np.array([0, 0, 3], np.float32), np.array([0, 0, -1], np.float32)
+    if kind == "cornell_v3":
+        out["lookfrom"], out["lookat"] = np.array([0, 0, 35], np.float32), np.array([0, 0, -10], np.float32)
     if kind == "cornell_v2":
         out["lookfrom"], out["lookat"] = np.array([0, 0, 35], np.float32), np.array([0, 0, -10], np.float32)
     if kind == "scene_demo":
@@ -609,6 +624,7 @@ FIXTURES = {
     # the other example scripts exactly as shipped (resolution and bounce cap of the files)
     "cornell_box_columns": (gen_columns, dict(kind="cornell_box", width=480, height=480, bounces=128, seed=0, columns=[0, 120, 239, 240, 300, 479])),
     "cornell_v2_columns": (gen_columns, dict(kind="cornell_v2", width=512, height=512, bounces=3, seed=0, columns=[0, 100, 255, 256, 300, 400, 450, 511])),
+    "cornell_v3_columns": (gen_columns, dict(kind="cornell_v3", width=512, height=512, bounces=3, seed=0, columns=[0, 100, 255, 256, 300, 400, 450, 511])),
     "scene_demo_columns": (gen_columns, dict(kind="scene_demo", width=480, height=270, bounces=128, seed=0, columns=[0, 100, 200, 239, 240, 300, 400, 479])),
     # the src/ package at its shipped resolution, 16 launches of pathtrace()
     "src_columns": (gen_src_columns, dict(width=768, height=432, launches=16, seed=0, columns=[0, 100, 250, 383, 384, 500, 640, 767])),
