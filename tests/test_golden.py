@@ -83,11 +83,11 @@ def test_product_host_code_matches_reference_source(path):
 
 
 # ---------------------------------------------------------------- BASELINE.json configurations at their real size
-# Spread columns of launch 0 (1 spp) of the full-resolution images, rendered by the reference's own source files under
+# Spread columns of launch 0 (1 spp; c1_columns_4spp: launches 0-3) of the full-resolution images, rendered by the reference's own source files under
 # the stand-in (tests/tools/gen_golden.py *_columns): configs[0] 256^2 / 4 bounces, configs[1] 1024^2 / 8 bounces,
 # configs[4] 4096^2 / 8 bounces (cornell_box_shortest.py), configs[3] 1920 x 1080 / 8 bounces (tokyo_ibl.py) and
 # configs[2] 1024^2 / 16 bounces, frame 0 (bunny_sdf_glass.py).
-REAL_SIZE = {"c0_columns": (256, 256, 4), "c1_columns": (1024, 1024, 8), "c4_columns": (4096, 4096, 8), "c3_columns": (1920, 1080, 8),
+REAL_SIZE = {"c0_columns": (256, 256, 4), "c1_columns": (1024, 1024, 8), "c1_columns_4spp": (1024, 1024, 8), "c4_columns": (4096, 4096, 8), "c3_columns": (1920, 1080, 8),
              "c2_columns": (1024, 1024, 16),
              # the remaining example scripts exactly as shipped (resolution and bounce cap of the files)
              "cornell_box_columns": (480, 480, 128), "cornell_v2_columns": (512, 512, 3), "cornell_v3_columns": (512, 512, 3),
@@ -99,9 +99,9 @@ def real_size_case(name):
     from raytracingpbr_b200 import scenes
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     W, H, B, S, seed = params(g)
-    assert (W, H, B) == REAL_SIZE[name] and S == 1              # exactly the configuration BASELINE.json names
+    assert (W, H, B) == REAL_SIZE[name]                         # exactly the configuration BASELINE.json names
     cols, want = g["columns"].astype(int), g["image_buffer_columns"]
-    assert want.shape == (len(cols), H, 4) and (want[..., 3] == 1.0).all()
+    assert want.shape == (len(cols), H, 4) and (want[..., 3] == float(S)).all()
     assert len(np.unique(want[..., :3])) > 10 and (want[..., :3].sum(-1) > 0).mean() > 0.05     # a real image, not zeros
     env = None
     if name == "c3_columns":
@@ -119,7 +119,7 @@ def real_size_case(name):
         env = common.env_table(g["env_u8"], 1.8, 2.2)               # bunny_sdf_glass.py:279-280
     else:
         cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=seed)
-    return cfg, objs, cam, tm, env, cols, want
+    return cfg, objs, cam, tm, env, cols, want, S
 
 
 def test_configs0_fixture_present():
@@ -128,32 +128,32 @@ def test_configs0_fixture_present():
 
 @pytest.mark.parametrize("name", REAL_SIZE_PRESENT)
 def test_oracle_matches_reference_source_at_real_size(name):
-    cfg, objs, cam, tm, env, cols, want = real_size_case(name)
+    cfg, objs, cam, tm, env, cols, want, spp = real_size_case(name)
     oc, oo = common.to_oracle(cfg, cam, objs)
     buf = np.zeros((cfg.width, cfg.height, 4), np.float32)
     for c0 in cols:                                             # the oracle renders single columns of the full image
-        po.pathtrace(oc, oo, 1, env=env, i0=int(c0), i1=int(c0) + 1, image_buffer=buf)
+        po.pathtrace(oc, oo, spp, env=env, i0=int(c0), i1=int(c0) + 1, image_buffer=buf)
     assert np.array_equal(buf[cols], want), name
 
 
 @pytest.mark.parametrize("name", [n for n in REAL_SIZE_PRESENT if n not in ("c4_columns", "c2_columns")])   # (whole images: keep the CPU suite short)
 def test_product_host_code_matches_reference_source_at_real_size(name):
-    cfg, objs, cam, tm, env, cols, want = real_size_case(name)
-    assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, 1, env=env)[cols], want)
+    cfg, objs, cam, tm, env, cols, want, spp = real_size_case(name)
+    assert np.array_equal(common.hostcheck_pathtrace(cfg, cam, objs, spp, env=env)[cols], want)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", REAL_SIZE_PRESENT)
 def test_cuda_matches_reference_source_at_real_size(name):
     from raytracingpbr_b200 import PathTracer, _native as N
-    cfg, objs, cam, tm, env, cols, want = real_size_case(name)
+    cfg, objs, cam, tm, env, cols, want, spp = real_size_case(name)
     for kernel in (N.KERNEL_PERSISTENT, N.KERNEL_SIMPLE):
         cfg.kernel = kernel
         with PathTracer(cfg, objs, cam, tm) as pt:
             if env is not None:
                 pt.set_envmap(env)
             pt.refresh()
-            pt.pathtrace(1)
+            pt.pathtrace(spp)                                   # all the reference's launches in ONE kernel launch
             buf = pt.image_buffer.to_numpy()
         assert np.array_equal(buf[cols], want), (name, kernel)
 

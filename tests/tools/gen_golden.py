@@ -142,7 +142,7 @@ def gen_shortest(name, width, height, bounces, spp, seed):
 
 # ------------------------------------------------------------------------------ families B / C
 def _columns_worker(job):
-    kind, name, width, height, bounces, seed, cols = job
+    kind, name, width, height, bounces, seed, cols, spp = job
     want = set(cols)
     install_rng(seed)
     if kind == "shortest":
@@ -199,21 +199,22 @@ def _columns_worker(job):
     else:
         raise KeyError(kind)
     ti.pixel_filter = lambda i, j: i in want
-    ti.rng.launch = 0
-    run()
+    for launch in range(spp):          # the reference's main loop: one launch per sample, image_buffer += (colour, 1)
+        ti.rng.launch = launch
+        run()
     ti.pixel_filter = None
     buf = m.image_buffer.to_numpy()
     return cols, buf[cols]
 
 
-def gen_columns(name, kind, width, height, bounces, seed, columns, workers=8):
+def gen_columns(name, kind, width, height, bounces, seed, columns, workers=8, spp=1):
     """A BASELINE.json configuration at its REAL resolution and bounce count, launch 0 (1 spp), for a spread subset of
     image columns: the scalar stand-in needs ~0.3 s per sample, pixels are independent and the RNG stream is keyed by
     the global pixel index, so a column subset of the full image is exact."""
     import multiprocessing as mp
     t0 = time.time()
     columns = sorted(columns)
-    jobs = [(kind, name, width, height, bounces, seed, columns[k::workers]) for k in range(workers) if columns[k::workers]]
+    jobs = [(kind, name, width, height, bounces, seed, columns[k::workers], spp) for k in range(workers) if columns[k::workers]]
     with mp.get_context("fork").Pool(len(jobs)) as pool:
         parts = pool.map(_columns_worker, jobs)
     img = np.zeros((len(columns), height, 4), np.float32)
@@ -221,7 +222,7 @@ def gen_columns(name, kind, width, height, bounces, seed, columns, workers=8):
         for c, d in zip(cols, data):
             img[columns.index(c)] = d
     print(f"  {name}: {len(columns)} columns of {width}x{height} in {time.time() - t0:.1f} s")
-    out = {"width": width, "height": height, "bounces": bounces, "spp": 1, "seed": seed,
+    out = {"width": width, "height": height, "bounces": bounces, "spp": spp, "seed": seed,
            "columns": np.asarray(columns, np.int32), "image_buffer_columns": img}
     if kind == "tokyo":
         out["env_u8"] = synthetic_env()
@@ -615,6 +616,8 @@ FIXTURES = {
     # configs[1] / configs[4]: the same scene at 1024^2 and 4096^2 with 8 bounces; configs[3]: tokyo_ibl at 1920 x 1080, 8 bounces
     "c1_columns": (gen_columns, dict(kind="shortest", width=1024, height=1024, bounces=8, seed=0,
                                      columns=[0, 255, 400, 511, 512, 640, 900, 1023])),
+    "c1_columns_4spp": (gen_columns, dict(kind="shortest", width=1024, height=1024, bounces=8, seed=0, spp=4,
+                                          columns=[64, 200, 330, 470, 555, 690, 820, 960])),
     "c4_columns": (gen_columns, dict(kind="shortest", width=4096, height=4096, bounces=8, seed=0, columns=[1500, 2047])),
     # configs[2]: bunny_sdf_glass.py at 1024 x 1024, 16 bounces, frame 0 (the neural SDF costs seconds per sample here)
     "c2_columns": (gen_columns, dict(kind="bunny", width=1024, height=1024, bounces=16, seed=0,
