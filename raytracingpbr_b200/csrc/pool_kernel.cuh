@@ -40,13 +40,14 @@ constexpr unsigned kFull = 0xffffffffu;
 // kernel and to the CPU oracle.
 // ------------------------------------------------------------------------------------------
 enum : int { ST_NONE = 0, ST_READY = 1, ST_HIT = 2, ST_MISS = 3, ST_DONE = 4, ST_FETCH = 5, ST_NEWPATH = 6,
-             ST_ADVANCE = 7, ST_DEAD = 8 };
+             ST_ADVANCE = 7, ST_DEAD = 8, ST_SLOW = 9 };
 
 // slot fields (word index into the per-warp SoA)
 enum : int { F_ROX = 0, F_ROY, F_ROZ, F_RDX, F_RDY, F_RDZ, F_COLX, F_COLY, F_COLZ, F_T, F_W, F_S, F_D, F_TEVAL,
              F_STEPS, F_IDX, F_DEPTH, F_RNGN, F_PIXEL, F_SAMP, F_K, F_STATUS, F_ACCX, F_ACCY, F_ACCZ, F_ACCW,
              F_COUNT };
 static_assert(F_COUNT == kPoolSlotWords, "kernels_config.h: kPoolSlotWords");
+constexpr int F_TSTOP = F_IDX;   // families A/B (the argmin is re-evaluated at the hit): the ray's t_stop, see ray_t_stop()
 // per-warp work-queue chunk (words after the two stacks)
 enum : int { WQ_LO = 0, WQ_HI, WQ_LEFT, WQ_ITEM, WQ_SAMP, WQ_NFRESH, WQ_COUNT };
 static_assert(WQ_COUNT <= kPoolQueueWords, "kernels_config.h: kPoolQueueWords");
@@ -79,6 +80,9 @@ __device__ __forceinline__ void load_march(const Pool<NSLOT>& pool, int slot, Ma
     if (VAR::MARCHER != MARCH_PLAIN) {
         m.w = pool.getf(F_W, slot); m.s = pool.getf(F_S, slot); m.d = pool.getf(F_D, slot);
     }
+#if defined(RT_JIT_BBOX)
+    if (VAR::MARCHER != MARCH_SRC) m.t_stop = pool.getf(F_TSTOP, slot);
+#endif
 }
 template <class VAR, int NSLOT>
 __device__ __forceinline__ void load_finished(const Pool<NSLOT>& pool, int slot, MarchState& m)
@@ -109,6 +113,9 @@ __device__ __forceinline__ void store_ready(Pool<NSLOT>& pool, int slot, const M
     pool.setf(F_RDX, slot, m.rd.x); pool.setf(F_RDY, slot, m.rd.y); pool.setf(F_RDZ, slot, m.rd.z);
     pool.setf(F_T, slot, m.t);
     pool.seti(F_STEPS, slot, m.steps);
+#if defined(RT_JIT_BBOX)
+    if (VAR::MARCHER != MARCH_SRC) pool.setf(F_TSTOP, slot, m.t_stop);
+#endif
     if (VAR::MARCHER != MARCH_PLAIN) {
         pool.setf(F_W, slot, m.w); pool.setf(F_S, slot, m.s); pool.setf(F_D, slot, m.d);
     }
@@ -138,7 +145,7 @@ __device__ __forceinline__ void zero_march(MarchState& m)
 {
     idle_march(m);
     m.t = 0.0f; m.w = 1.0f; m.s = 0.0f; m.d = 0.0f; m.t_eval = 0.0f;
-    m.steps = 0; m.idx = 0;
+    m.steps = 0; m.idx = 0; m.t_stop = 3.0e38f;
 }
 
 // One resolve batch: every lane with slot >= 0 runs its slot's state machine (surface interaction, sample
@@ -170,6 +177,10 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
     p.rng = rng_make(0u, 0u, 0u);
     if (slot >= 0) {
         st = pool.geti(F_STATUS, slot);
+#if defined(RT_JIT_FAST)
+        if (st == ST_SLOW) load_march<VAR, NSLOT>(pool, slot, p.m);   // dropped out of the march loop: the march goes on here
+        else
+#endif
         load_finished<VAR, NSLOT>(pool, slot, p.m);
         p.col = V3(pool.getf(F_COLX, slot), pool.getf(F_COLY, slot), pool.getf(F_COLZ, slot));
         p.depth = pool.geti(F_DEPTH, slot);
@@ -188,6 +199,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
 
     // ---- run the slot's state machine until it needs marching again (or dies)
     for (;;) {
+        const int st_in = st;
         if (MODE == MODE_FRESH) {
             // regeneration batches carry no marched rays
         } else if (VAR::FAMILY != FAMILY_C) {
@@ -307,9 +319,23 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
             st = begin_bounce<VAR>(P, p) ? ST_READY : ST_DONE;
         }
 #if defined(RT_JIT_SCENE)
-        // irregular rays (non-finite origin / direction) never enter the specialised march loop
-        if (st == ST_READY && ray_is_irregular(p.m))
-            st = march_to_end_generic<VAR>(P, p.m) == MARCH_HIT ? ST_HIT : ST_MISS;
+        // A bounce has just begun (or, fast-region kernels, a lane dropped out of the march loop: ST_SLOW).
+        // Irregular rays (non-finite origin / direction) never enter the specialised march loop; the others get
+        // their t_stop (scene bounds) and take the steps that lie outside the fast region right here.
+        {
+            const bool begun = st == ST_READY && st_in != ST_READY;
+            if (begun && ray_is_irregular(p.m)) {
+                st = march_to_end_generic<VAR>(P, p.m) == MARCH_HIT ? ST_HIT : ST_MISS;
+            } else if (begun || st == ST_SLOW) {
+#if defined(RT_JIT_BBOX)
+                if (begun) p.m.t_stop = ray_t_stop<VAR>(P, p.m);
+#endif
+#if defined(RT_JIT_FAST)
+                const int pre = slow_march<VAR>(P, p.m);
+                st = pre == MARCH_CONTINUE ? ST_READY : (pre == MARCH_HIT ? ST_HIT : ST_MISS);
+#endif
+            }
+        }
         const bool more = MODE == MODE_FRESH ? (st == ST_DONE || st == ST_FETCH)       // (irregular new rays go to the pending stack)
                         : MODE == MODE_HITS  ? (st == ST_HIT || st == ST_MISS || st == ST_DONE)
                         : st == ST_HIT || st == ST_MISS || (VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE));
@@ -469,6 +495,7 @@ __device__ __forceinline__ void pool_body(const KParams& P)
         // dummy ray (idle_march) and are masked out of the vote, which keeps the loop body branch-free.
         unsigned fin;
         float aux;
+        bool slow = false;   // fast-region kernels: the lane's next evaluation point lies outside the region
 #if defined(RT_JIT_SPLIT_BUNNY)
         // Scenes with the neural bunny: a step is cheap outside the bunny's unit sphere (|p| - 0.8 and the
         // analytic objects) and ~1700 instructions inside (the MLP).  Marching them in lockstep left a third
@@ -497,14 +524,14 @@ __device__ __forceinline__ void pool_body(const KParams& P)
         // tuning knob (RTPBR_MARCH_UNROLL=2): vote after every second step; a lane whose march ends on the first
         // one sits the second one out
         do {
-            bool f = march_step_fin<VAR>(P, m, aux);
-            if (!f) f = march_step_fin<VAR>(P, m, aux);
+            bool f = march_step_fin<VAR>(P, m, aux, slow);
+            if (!f) f = march_step_fin<VAR>(P, m, aux, slow);
             fin = __ballot_sync(kFull, f && my >= 0);
         } while (fin == 0u);
 #else
         do {
             if (VAR::COUNT) { c_iters += 32; c_active += (unsigned long long)__popc(active); }
-            const bool f = march_step_fin<VAR>(P, m, aux);
+            const bool f = march_step_fin<VAR>(P, m, aux, slow);
             fin = __ballot_sync(kFull, f && my >= 0);
         } while (fin == 0u);
 #endif
@@ -516,6 +543,12 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             const int nf = __popc(fin);
             if ((fin >> lane) & 1u) {
                 const int r = __popc(fin & lane_lt);
+#if defined(RT_JIT_FAST)
+                if (march_undo_slow<VAR>(m, aux, slow)) {          // nothing was advanced: the slot keeps its march state and goes on in the resolve phase
+                    store_parked<VAR, NSLOT>(pool, my, m);
+                    pool.seti(F_STATUS, my, ST_SLOW);
+                } else
+#endif
                 store_finished<VAR, NSLOT>(pool, my, m, march_status<VAR>(P, aux) == MARCH_HIT ? ST_HIT : ST_MISS);
                 pend[n_pend + r] = (uint8_t)my;
                 if (r < n_ready) {

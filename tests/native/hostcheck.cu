@@ -8,11 +8,96 @@
 
 #include "../../include/rtpbr.h"
 #include "../../raytracingpbr_b200/csrc/host_setup.h"
+// tests/test_jit.py compiles this file a second time per scene with the scene-specialised translation unit that
+// jit_codegen.h generates: HC_JIT_PREAMBLE = its #defines, HC_JIT_BODY = its functions.  trace_sample() then marches
+// the way the specialised pool kernel does (fast region, t_stop), on the CPU.
+#if defined(HC_JIT_PREAMBLE)
+#include HC_JIT_PREAMBLE
+#endif
 #include "../../raytracingpbr_b200/csrc/rt_integrator.cuh"
+#if defined(HC_JIT_BODY)
+namespace rt {
+#include HC_JIT_BODY
+}
+#endif
 
 using namespace rt;
 
 #define HC_API extern "C" __attribute__((visibility("default")))
+
+#if defined(RT_JIT_SCENE)
+template <class VAR>
+static int jit_march_check_t(const KParams& P, const float* rays, int nrays, int* out)
+{
+    int bad = 0;
+    for (int k = 0; k < nrays; ++k) {
+        MarchState a, b;
+        memset(&a, 0, sizeof(a));
+        a.ro = V3(rays[6 * k], rays[6 * k + 1], rays[6 * k + 2]);
+        a.rd = V3(rays[6 * k + 3], rays[6 * k + 4], rays[6 * k + 5]);
+        if (ray_is_irregular(a)) continue;
+        march_begin<VAR>(P, a);
+        b = a;
+        int sa;
+        do { sa = march_step<VAR, true>(P, a); } while (sa == MARCH_CONTINUE);      // the generic code, to the end
+        const int sb = march_to_end_jit<VAR>(P, b);
+        bool same = sa == sb;
+        if (same && sa == MARCH_HIT) {
+            const vec3 pa = hit_position<VAR>(a), pb = hit_position<VAR>(b);
+            same = memcmp(&pa, &pb, sizeof(pa)) == 0;
+            if (VAR::MARCHER == MARCH_SRC) same = same && a.idx == b.idx;
+        }
+        if (!same) ++bad;
+        out[0] += sa == MARCH_HIT;
+        out[1] += a.steps;
+        out[2] += b.steps;
+    }
+    return bad;
+}
+// rays: (origin, direction) x nrays.  Returns the number of rays whose specialised march ends differently from the generic
+// one (status; hit position bits); out = { hits, generic steps, specialised steps }.
+HC_API int hostcheck_jit_march(const RtpbrConfig* cfg, const RtpbrObject* objs, int n, int frame, const float* rays, int nrays, int* out)
+{
+    KParams P;
+    memset(&P, 0, sizeof(P));
+    fill_config(P, *cfg);
+    fill_objects(P, objs, n);
+    fill_frame(P, frame);
+    out[0] = out[1] = out[2] = 0;
+    bool bunny = false;
+    for (int k = 0; k < n; ++k) bunny = bunny || objs[k].type == RTPBR_SHAPE_BUNNY;
+    if (cfg->family == RTPBR_FAMILY_A) return jit_march_check_t<Variant<FAMILY_A, 0, SHAPESET_BOX, MARCH_PLAIN, false>>(P, rays, nrays, out);
+    if (cfg->family == RTPBR_FAMILY_B && cfg->marcher == RTPBR_MARCH_PLAIN) return jit_march_check_t<Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_PLAIN, false>>(P, rays, nrays, out);
+    if (cfg->family == RTPBR_FAMILY_B && bunny) return jit_march_check_t<Variant<FAMILY_B, 0, SHAPESET_BUNNY, MARCH_ENHANCED, false>>(P, rays, nrays, out);
+    if (cfg->family == RTPBR_FAMILY_B) return jit_march_check_t<Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_ENHANCED, false>>(P, rays, nrays, out);
+    return jit_march_check_t<Variant<FAMILY_C, 0, SHAPESET_ANALYTIC, MARCH_SRC, false>>(P, rays, nrays, out);
+}
+// points x npts: wherever jit_nearest_fast() says ok its result must have the bits of jit_nearest_dist().  Returns the
+// number of violations, -1 when the scene has no fast region; *n_ok = points inside the region.
+HC_API int hostcheck_jit_fast(const RtpbrConfig* cfg, const RtpbrObject* objs, int n, int frame, const float* pts, int npts, int* n_ok)
+{
+    *n_ok = 0;
+#if defined(RT_JIT_FAST)
+    KParams P;
+    memset(&P, 0, sizeof(P));
+    fill_config(P, *cfg);
+    fill_objects(P, objs, n);
+    fill_frame(P, frame);
+    int bad = 0;
+    for (int k = 0; k < npts; ++k) {
+        const vec3 p = V3(pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]);
+        bool ok;
+        const float f = jit_nearest_fast(P, p, ok), d = jit_nearest_dist(P, p);
+        if (!ok) continue;
+        ++*n_ok;
+        if (memcmp(&f, &d, 4) != 0) ++bad;
+    }
+    return bad;
+#else
+    return -1;
+#endif
+}
+#endif
 
 template <class VAR>
 static void run(const KParams& P, float4* buf)

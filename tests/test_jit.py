@@ -167,13 +167,116 @@ def test_specialised_source_carries_the_right_variant_switches():
     a, cfg = src_of(scenes.cornell_box_shortest)
     assert "#define RT_K_MAX_STEPS %d\n" % cfg.max_steps in a and "#define RT_K_HIT_EPS" in a and "#define RT_K_T_FAR" in a
     assert "RT_RESOLVE_OOL" not in a and "RT_JIT_SPLIT_BUNNY" not in a and "jit_nearest_partial" not in a
-    assert a.count("sd_box2_ranged_x2<false>") == 8                      # 4 packed pairs x (jit_nearest, jit_nearest_dist)
+    assert a.count("sd_box2_ranged_x2<false>") == 9                      # 4 packed pairs x (jit_nearest, jit_nearest_dist) + 1 in jit_nearest_fast
+    assert "#define RT_JIT_FAST 1" in a and "#define RT_JIT_BBOX 1" in a  # five walls as planes; bounded scene
     for preset in (scenes.tokyo_ibl, scenes.cornell_box, scenes.cornell_box_v3, scenes.src_scene):
         b, _ = src_of(preset)
         assert "#define RT_RESOLVE_OOL 1" in b and "RT_JIT_SPLIT_BUNNY" not in b
     c, _ = src_of(scenes.bunny_glass)
     assert "#define RT_JIT_SPLIT_BUNNY 1" in c and "RT_RESOLVE_OOL" not in c
     assert "jit_nearest_partial(const KParams& P, vec3 pos, bool& need_mlp, vec3& pb)" in c and "rt_inf()" in c
+
+
+# ---- the specialised MARCH (fast region = walls as planes, t_stop = provable misses), compiled for the host ----------
+_JIT_HC = {}
+
+
+def jit_hostcheck(name, tmp_path_factory):
+    """tests/native/hostcheck.cu compiled together with the scene-specialised translation unit of preset `name`."""
+    if name in _JIT_HC:
+        return _JIT_HC[name]
+    preset = PRESETS[name][0]
+    cfg, objs, cam, _ = preset(40, 32, seed=5, max_bounces=6)
+    src = N.jit_source(cfg, [o.to_native() for o in objs])
+    d = tmp_path_factory.mktemp("jit_hc_" + name)
+    pre = src[:src.index('#include "pool_kernel.cuh"')]
+    body = src[src.index("namespace rt {") + len("namespace rt {"):src.index("}  // namespace rt")]
+    (d / "preamble.h").write_text(pre)
+    (d / "body.inc").write_text(body)
+    so = d / "libhostcheck_jit.so"
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Wno-deprecated-gpu-targets",
+                           f'-DHC_JIT_PREAMBLE="{d}/preamble.h"', f'-DHC_JIT_BODY="{d}/body.inc"', "-Xcompiler",
+                           "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma,-fopenmp,-fvisibility=hidden", "-o", str(so),
+                           os.path.join(common.ROOT, "tests", "native", "hostcheck.cu"), "-lgomp"], stderr=subprocess.DEVNULL)
+    L = C.CDLL(str(so))
+    _JIT_HC[name] = (L, src, cfg, objs, cam)
+    return _JIT_HC[name]
+
+
+def _native_objects(objs):
+    nat = [o.to_native() for o in objs]
+    return (N.RtpbrObject * len(nat))(*nat), len(nat)
+
+
+@pytest.mark.parametrize("name", list(PRESETS))
+def test_specialised_march_ends_like_the_generic_one(name, tmp_path_factory):
+    """Random rays through every preset: status and hit position of march_to_end_jit() (the pieces the pool kernel
+    interleaves: t_stop from the scene bounds, full-code steps outside the fast region, the fast step inside) equal the
+    generic march's, bit for bit; where the scene is bounded the specialised march takes fewer steps."""
+    L, src, cfg, objs, cam = jit_hostcheck(name, tmp_path_factory)
+    extent = PRESETS[name][2]
+    rng = np.random.default_rng(23)
+    n = 12000 if name != "bunny_glass" else 2500
+    o = rng.uniform(-extent, extent, (n, 3))
+    o[: n // 4] = np.asarray(cam.lookfrom, np.float64)                      # camera rays
+    o[n // 4: n // 2] *= 0.3                                                 # origins well inside the scene
+    d = rng.normal(size=(n, 3))
+    d[: n // 4] = np.asarray(cam.lookat, np.float64) - np.asarray(cam.lookfrom, np.float64) + rng.normal(size=(n // 4, 3)) * 0.25
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[-50:, rng.integers(0, 3, 50)] = 0.0                                    # axis-parallel components
+    rays = np.concatenate([o, d], axis=1).astype(np.float32)
+    arr, nobj = _native_objects(objs)
+    out = (C.c_int * 3)()
+    bad = L.hostcheck_jit_march(C.byref(cfg), arr, nobj, 3, rays.ctypes.data_as(C.POINTER(C.c_float)), n, out)
+    assert bad == 0
+    hits, steps_generic, steps_jit = out[0], out[1], out[2]
+    assert 0.05 * n < hits < 0.98 * n                                        # both outcomes are exercised
+    if "#define RT_JIT_BBOX 1" in src:
+        assert steps_jit < steps_generic                                     # provable misses end early
+    else:
+        assert steps_jit == steps_generic
+
+
+@pytest.mark.parametrize("name", ["cornell_box_shortest", "cornell_box", "cornell_box_v3"])
+def test_walls_as_planes_have_the_bits_of_the_box_distance(name, tmp_path_factory):
+    L, src, cfg, objs, cam = jit_hostcheck(name, tmp_path_factory)
+    assert "#define RT_JIT_FAST 1" in src
+    scale = 10.0 if name == "cornell_box_v3" else 1.0
+    rng = np.random.default_rng(29)
+    pts = rng.uniform(-1.05, 1.05, (40000, 3))
+    pts[:10000] = np.clip(pts[:10000], -0.8, 0.8)                            # inside the room ...
+    k = rng.integers(0, 3, 10000)
+    pts[np.arange(10000), k] = np.sign(pts[np.arange(10000), k]) * (0.8 - np.abs(rng.normal(size=10000)) * 1e-5)   # ... hugging a wall
+    pts = (pts * scale).astype(np.float32)
+    arr, nobj = _native_objects(objs)
+    n_ok = C.c_int(0)
+    bad = L.hostcheck_jit_fast(C.byref(cfg), arr, nobj, 0, pts.ctypes.data_as(C.POINTER(C.c_float)), len(pts), C.byref(n_ok))
+    assert bad == 0
+    assert n_ok.value > 15000                                                # the region covers the room
+
+
+@pytest.mark.parametrize("name", list(PRESETS))
+def test_specialised_march_renders_the_same_image_on_host(name, tmp_path_factory):
+    """Whole paths: trace_sample() with the specialised march against the generic build of the same harness."""
+    L, src, cfg, objs, cam = jit_hostcheck(name, tmp_path_factory)
+    if cfg.family == N.FAMILY_C:
+        pytest.skip("family C: the specialised kernel changes nearest() only (covered above)")
+    env = None
+    if cfg.sky == N.SKY_ENVMAP:
+        env = common.env_table(np.random.default_rng(1).integers(0, 256, (16, 8, 3), dtype=np.uint8), 1.4, 2.2)
+    want = common.hostcheck_pathtrace(cfg, cam, objs, 3, env=env, frame=3)
+    f32p = C.POINTER(C.c_float)
+    L.hostcheck_pathtrace_ex.restype = C.c_int
+    L.hostcheck_pathtrace_ex.argtypes = common.hostcheck().hostcheck_pathtrace_ex.argtypes
+    arr, nobj = _native_objects(objs)
+    got = np.zeros((cfg.width, cfg.height, 4), np.float32)
+    ncam = cam.to_native()
+    rc = L.hostcheck_pathtrace_ex(C.byref(cfg), C.byref(ncam), arr, nobj, got.ctypes.data_as(f32p), None,
+                                  env.ctypes.data_as(f32p) if env is not None else None,
+                                  env.shape[0] if env is not None else 0, env.shape[1] if env is not None else 0,
+                                  3, 3, 0, 0, 1, 32, None)
+    assert rc == 0
+    assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("name", list(PRESETS))
