@@ -105,6 +105,8 @@ struct RtpbrContext {
     int jit_blocks_per_sm = 0;
     int jit_block = rt::kPoolBlock, jit_slots = rt::kPoolSlots, jit_min_blocks = rt::kPoolMinBlocks;   // pool geometry of the NVRTC build
     std::string jit_log = "not built yet";
+    std::string jit_key;          // generated source + build options of the loaded kernel
+    int jit_churn = 0;            // recent NVRTC compiles (decays per pathtrace): animated scenes fall back to the ahead-of-time kernel
     void* nccl_comm = nullptr;
     int nccl_rank = 0, nccl_nranks = 1;
     unsigned long long launches = 0;
@@ -184,9 +186,6 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     rt::fill_shard(c->P, 0, 1, 32);
     rt::fill_frame(c->P, 0);
     if (const char* j = getenv("RTPBR_JIT")) c->jit_enabled = atoi(j) != 0;
-    if (const char* v = getenv("RTPBR_POOL_SLOTS")) { int x = atoi(v); if (x >= 32 && x <= 128 && x % 4 == 0) c->jit_slots = x; }
-    if (const char* v = getenv("RTPBR_POOL_BLOCK")) { int x = atoi(v); if (x >= 32 && x <= 1024 && x % 32 == 0) c->jit_block = x; }
-    if (const char* v = getenv("RTPBR_POOL_MIN_BLOCKS")) { int x = atoi(v); if (x >= 1 && x <= 16) c->jit_min_blocks = x; }
     c->P.resolve_min = 8;
     if (const char* q = getenv("RTPBR_RESOLVE_MIN")) {
         int v = atoi(q);
@@ -243,6 +242,7 @@ int rtpbr_destroy(RtpbrContext* c)
     if (!c) return RTPBR_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    c->jit_kernel.reset();
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     for (auto& p : c->kernel_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -280,12 +280,24 @@ int rtpbr_set_scene(RtpbrContext* c, const RtpbrObject* objects, int n)
     if (!rt::kernel_supported(sel))
         return fail(RTPBR_ERR_UNSUPPORTED, "no kernel variant for this family / marcher / shape combination "
                                            "(the neural bunny needs family B with the enhanced marcher)");
+    // The specialised kernel bakes the GEOMETRY into its instruction stream (materials stay in the parameter block):
+    // re-uploading an unchanged scene, or changing materials only, keeps the loaded kernel.
+    bool same_geometry = c->have_scene && (int)c->scene.size() == n;
+    for (int k = 0; k < n && same_geometry; ++k) {
+        const RtpbrObject& a = c->scene[k];
+        const RtpbrObject& b = objects[k];
+        same_geometry = a.type == b.type && memcmp(a.position, b.position, sizeof(a.position)) == 0 &&
+                        memcmp(a.rotation, b.rotation, sizeof(a.rotation)) == 0 && memcmp(a.scale, b.scale, sizeof(a.scale)) == 0;
+    }
     rt::fill_objects(c->P, objects, n);
     c->has_bunny = bunny;
     c->scene.assign(objects, objects + n);
-    c->jit_stale = true;
+    if (!same_geometry) {
+        if (c->have_scene && c->jit_churn < 24) c->jit_churn += 2;   // see ensure_jit
+        c->jit_stale = true;
+        c->blocks_per_sm = 0;  // kernel variant may change with the object count
+    }
     c->have_scene = true;
-    c->blocks_per_sm = 0;  // kernel variant may change with the object count
     return RTPBR_OK;
 }
 
@@ -355,22 +367,53 @@ int rtpbr_refresh(RtpbrContext* c)
 // leaves the ahead-of-time kernel in charge; the reason is kept for rtpbr_jit_status().
 static void ensure_jit(RtpbrContext* c)
 {
+    if (c->jit_churn > 0) c->jit_churn--;
     if (!c->jit_enabled || !c->jit_stale) return;
+    if (c->cfg.count_work) {
+        c->jit_stale = false;
+        c->jit_kernel.reset();
+        c->jit_log = "disabled: count_work uses the ahead-of-time counting kernel";
+        return;
+    }
+    // A scene whose geometry changes every few launches (animation through set_scene) would pay ~2 s of NVRTC per
+    // frame: while that goes on the ahead-of-time kernel renders (same bits); the specialised one comes back once the
+    // geometry has been stable for a few launches.
+    if (c->jit_churn > 8) {
+        if (c->jit_kernel) { cudaStreamSynchronize(c->stream); c->jit_kernel.reset(); c->jit_key.clear(); }
+        c->jit_log = "geometry changes every few launches: ahead-of-time kernel until it settles";
+        c->blocks_per_sm = 0;
+        return;                                   // stays stale: retried at the next launch
+    }
     c->jit_stale = false;
-    c->jit_kernel.reset();
-    if (c->cfg.count_work) { c->jit_log = "disabled: count_work uses the ahead-of-time counting kernel"; return; }
     int max_pairs = 1 << 30;      // RTPBR_JIT_PAIRS: how many box pairs use the packed f32x2 form (tuning knob)
     if (const char* v = getenv("RTPBR_JIT_PAIRS")) max_pairs = atoi(v) < 0 ? 0 : atoi(v);
     const rt::jit::Source src = rt::jit::generate(c->cfg, c->scene.data(), (int)c->scene.size(), max_pairs);
     std::shared_ptr<std::vector<char>> cubin;
     std::string log;
+    // Pool geometry and scheduling policy of the NVRTC build.  Environment knobs win; otherwise kernels with a fast region
+    // (family A: short march step, small resolve phase) run 3 CTAs/SM x 80 slots per warp, regenerate paths in batches of
+    // their own and leave the march loop only when 6 lanes have finished (profiles/r02_sweeps.md); everything else keeps
+    // the ahead-of-time geometry.
+    auto env_int = [](const char* name, int lo, int hi, int dflt) {
+        const char* v = getenv(name);
+        if (!v || !*v) return dflt;
+        const int x = atoi(v);
+        return x >= lo && x <= hi ? x : dflt;
+    };
+    c->jit_slots = env_int("RTPBR_POOL_SLOTS", 32, 128, src.fast ? 80 : rt::kPoolSlots);
+    if (c->jit_slots % 4 != 0) c->jit_slots = rt::kPoolSlots;
+    c->jit_block = env_int("RTPBR_POOL_BLOCK", 32, 1024, rt::kPoolBlock);
+    if (c->jit_block % 32 != 0) c->jit_block = rt::kPoolBlock;
+    c->jit_min_blocks = env_int("RTPBR_POOL_MIN_BLOCKS", 1, 16, src.fast ? 3 : rt::kPoolMinBlocks);
+    const int regen_min = env_int("RTPBR_REGEN_MIN", 0, 32, src.fast ? 24 : 0);
+    const int regen_idle = env_int("RTPBR_REGEN_IDLE", 1, 32, src.fast ? 8 : 1);
+    const int fin_min = env_int("RTPBR_FIN_MIN", 1, 32, src.fast ? 6 : 1);
     const size_t smem = rt::pool_smem_bytes_for(c->jit_block, c->jit_slots);
     std::vector<std::string> defs = { "-DRT_POOL_BLOCK=" + std::to_string(c->jit_block), "-DRT_POOL_SLOTS=" + std::to_string(c->jit_slots),
                                       "-DRT_POOL_MIN_BLOCKS=" + std::to_string(c->jit_min_blocks) };
-    if (const char* v = getenv("RTPBR_REGEN_MIN")) {
-        const int x = atoi(v);
-        if (x >= 1 && x <= 32) defs.push_back("-DRT_REGEN_MIN=" + std::to_string(x));
-    }
+    if (regen_min > 0) defs.push_back("-DRT_REGEN_MIN=" + std::to_string(regen_min));
+    if (regen_idle > 1) defs.push_back("-DRT_REGEN_IDLE=" + std::to_string(regen_idle));
+    if (fin_min > 1) defs.push_back("-DRT_FIN_MIN=" + std::to_string(fin_min));
     if (const char* v = getenv("RTPBR_MARCH_UNROLL")) {
         if (atoi(v) == 2) defs.push_back("-DRT_MARCH_VOTE_EVERY_2=1");
     }
@@ -378,6 +421,14 @@ static void ensure_jit(RtpbrContext* c)
         const int x = atoi(v);
         if (x >= 1 && x <= 16) defs.push_back("-DRT_POOL_MIN_BLOCKS_BUNNY=" + std::to_string(x));
     }
+    std::string key = src.text;
+    for (const std::string& d : defs) key += "\n" + d;
+    if (c->jit_kernel && key == c->jit_key) return;          // same translation unit as the loaded kernel
+    if (c->jit_kernel) {
+        cudaStreamSynchronize(c->stream);                    // launches of the old module may still be queued
+        c->jit_kernel.reset();
+    }
+    c->jit_key.clear();
     if (!rt::jit::compile(src.text, rt::jit::default_include_dir(), cubin, log, defs)) {
         c->jit_enabled = false;
         c->jit_log = "NVRTC failed, using the ahead-of-time kernel: " + log;
@@ -397,6 +448,8 @@ static void ensure_jit(RtpbrContext* c)
                  std::to_string(c->jit_blocks_per_sm) + " CTAs/SM x " + std::to_string(c->jit_block) + " threads, " +
                  std::to_string(c->jit_slots) + " slots/warp)";
     c->jit_kernel = std::move(k);
+    c->jit_key = key;
+    if (log != "cached" && c->jit_churn < 24) c->jit_churn += 4;   // an actual NVRTC compile
 }
 
 static int launch_pool_chunk(RtpbrContext* c, const rt::KernelSelect& sel, std::pair<cudaEvent_t, cudaEvent_t>& ev,
@@ -435,8 +488,12 @@ static int launch_pool_chunk(RtpbrContext* c, const rt::KernelSelect& sel, std::
     return RTPBR_OK;
 }
 
+// Per-launch event pairs for rtpbr_kernel_time().  The pool is bounded: a caller that never collects (an interactive
+// render loop) wraps around after kMaxKernelEvents launches and overwrites the oldest pairs.
+constexpr size_t kMaxKernelEvents = 4096;
 static int next_event_pair(RtpbrContext* c, std::pair<cudaEvent_t, cudaEvent_t>** out)
 {
+    if (c->kernel_events_used == kMaxKernelEvents) c->kernel_events_used = 0;
     if (c->kernel_events_used == c->kernel_events.size()) {
         cudaEvent_t a, b;
         CUDA_TRY(cudaEventCreate(&a));
@@ -671,7 +728,13 @@ int rtpbr_set_jit(RtpbrContext* c, int enable)
     if (!c) return fail(RTPBR_ERR_ARG, "null context");
     c->jit_enabled = enable != 0;
     c->jit_stale = true;
-    if (!c->jit_enabled) { c->jit_kernel.reset(); c->jit_log = "disabled by rtpbr_set_jit"; c->blocks_per_sm = 0; }
+    if (!c->jit_enabled) {
+        if (c->jit_kernel) cudaStreamSynchronize(c->stream);
+        c->jit_kernel.reset();
+        c->jit_key.clear();
+        c->jit_log = "disabled by rtpbr_set_jit";
+        c->blocks_per_sm = 0;
+    }
     return RTPBR_OK;
 }
 
@@ -753,9 +816,12 @@ int rtpbr_reduce_tiles(RtpbrContext* c, int root)
 {
     if (!c) return fail(RTPBR_ERR_ARG, "null context");
     if (!c->nccl_comm) {
-        if (c->nccl_nranks == 1) return RTPBR_OK;
-        return fail(RTPBR_ERR_STATE, "rtpbr_nccl_init has not been called");
+        if (c->P.nranks == 1) return RTPBR_OK;                 // one rank owns every column: nothing to reduce
+        return fail(RTPBR_ERR_STATE, "this context renders one of " + std::to_string(c->P.nranks) +
+                                         " shards (rtpbr_set_shard) but rtpbr_nccl_init has not been called");
     }
+    if (c->P.nranks != c->nccl_nranks || c->P.rank != c->nccl_rank)
+        return fail(RTPBR_ERR_STATE, "rtpbr_set_shard and rtpbr_nccl_init disagree about rank / number of ranks");
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t count = npixels(c) * 4;
     int r;

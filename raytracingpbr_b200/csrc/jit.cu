@@ -165,6 +165,8 @@ bool compile(const std::string& source, const std::string& include_dir, std::sha
         if (FILE* f = fopen((std::string(dump) + ".cu").c_str(), "w")) { fwrite(source.data(), 1, source.size(), f); fclose(f); }
         if (FILE* f = fopen((std::string(dump) + ".cubin").c_str(), "wb")) { fwrite(out->data(), 1, out->size(), f); fclose(f); }
     }
+    // bounded: an animated scene produces a new translation unit per frame
+    if (g_cache.size() >= 64) g_cache.erase(g_cache.begin());
     g_cache[key] = out;
     cubin = out;
     log = plog;

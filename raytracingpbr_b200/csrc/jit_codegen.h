@@ -69,7 +69,17 @@ inline std::string row_expr(const float m[3], const char* const d[3])
 struct Source {
     std::string text;
     std::string kernel_name;
+    bool fast = false;     // jit_nearest_fast() + drop-out handling are compiled in (RT_JIT_FAST)
+    bool tstop = false;    // per-ray t_stop in the march loop (RT_JIT_TSTOP)
 };
+
+// Tuning / test knobs: unset = automatic, "0" = off, anything else = on wherever the analysis permits.
+inline int knob(const char* name)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return -1;
+    return atoi(v) != 0 ? 1 : 0;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Scene analysis
@@ -142,11 +152,11 @@ inline Analysis analyse(const RtpbrConfig& cfg, const RtpbrObject* objs, int n)
         !(cfg.relax_w0 >= 0.0f && cfg.relax_w0 <= 2.0f && cfg.relax_w_reset >= 0.0f && cfg.relax_w_reset <= 2.0f))
         A.bounded = false;
     if (!(cfg.hit_eps >= 0.0f && cfg.hit_eps < 0.25f && cfg.t_far > 0.0f && cfg.t_far < 1e30f)) A.bounded = false;
-    if (getenv("RTPBR_JIT_BBOX") && atoi(getenv("RTPBR_JIT_BBOX")) == 0) A.bounded = false;   // tuning / test knob
+    if (knob("RTPBR_JIT_BBOX") == 0) A.bounded = false;
 
     // ---- fast region: axis-aligned ("wall") boxes whose in-plane condition one region of space guarantees
     if (!have_box) return A;
-    if (getenv("RTPBR_JIT_FAST") && atoi(getenv("RTPBR_JIT_FAST")) == 0) return A;             // tuning / test knob
+    if (knob("RTPBR_JIT_FAST") == 0) return A;
     struct Cand { int object, normal; int world_axis[3]; double area; };
     std::vector<Cand> cands;
     for (int k = 0; k < n; ++k) {
@@ -416,6 +426,16 @@ inline Source generate(const RtpbrConfig& cfg, const RtpbrObject* objs, int n, i
     Analysis A = analyse(cfg, objs, n);
     if (cfg.family == RTPBR_FAMILY_C) { A.bounded = A.fast = false; A.walls.clear(); }   // src/: the marched origin is persisted in ray_buffer, every step counts
     if (bunnies == 1 && cfg.marcher == RTPBR_MARCH_ENHANCED) { A.fast = false; A.walls.clear(); }   // the two-stage bunny loop has its own cheap stage
+    // Where the analyses pay (measured on B200, profiles/r02_sweeps.md):
+    //   * the fast region wins 25 % on the diffuse-only family A, whose resolve phase is small; in the PBR families the
+    //     full-code steps of new camera paths (taken in the resolve phase, at ~4 lanes per batch) cost more than the
+    //     march loop saves (cornell_box.py 1244 -> 1032 Msamples/s), and the over-relaxed marcher steps INTO wall slabs
+    //     all the time (cornell_box_v3 1225 -> 752).  Automatic: family A only.
+    //   * t_stop costs a register and a slot word per ray and a dozen instructions per bounce: +7 % where most paths
+    //     end in the sky (bunny_sdf_glass), +1 % on tokyo_ibl, -5 % in a closed room (cornell_box.py).  Automatic: when
+    //     the scene has a sky (or is family A).
+    if (A.fast && knob("RTPBR_JIT_FAST") < 0 && cfg.family != RTPBR_FAMILY_A) { A.fast = false; A.walls.clear(); }
+    if (A.bounded && knob("RTPBR_JIT_BBOX") < 0 && cfg.family != RTPBR_FAMILY_A && cfg.sky == RTPBR_SKY_BLACK) A.bounded = false;
 
     Emitter E{ cfg, objs, n, round_of(cfg), max_pairs, std::string() };
     std::string& s = E.s;
@@ -433,6 +453,10 @@ inline Source generate(const RtpbrConfig& cfg, const RtpbrObject* objs, int n, i
         s += "#define RT_BB_SCALE " + flit((float)A.scale) + "\n";
     }
     if (A.fast) s += "#define RT_JIT_FAST 1\n";
+    // per-ray t_stop in the march loop: always without a fast region; with one, the same test runs where rays drop out
+    // of the region (slow_march) unless RTPBR_JIT_TSTOP=1 (tuning knob)
+    const bool tstop = A.bounded && (!A.fast || knob("RTPBR_JIT_TSTOP") == 1);
+    if (tstop && A.fast) s += "#define RT_JIT_TSTOP 1\n";
     // bunny scenes with the enhanced marcher: the march loop runs the cheap part of nearest() and the MLP
     // as separate stages (pool_kernel.cuh), which needs the third form of the function (mode -1); the split keeps
     // ONE (need_mlp, pb) pair, so it is used for scenes with exactly one bunny
@@ -453,6 +477,8 @@ inline Source generate(const RtpbrConfig& cfg, const RtpbrObject* objs, int n, i
     Source out;
     out.text = s;
     out.kernel_name = "k_pathtrace_pool_jit";
+    out.fast = A.fast;
+    out.tstop = tstop;
     return out;
 }
 

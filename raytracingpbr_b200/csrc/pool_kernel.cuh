@@ -80,7 +80,7 @@ __device__ __forceinline__ void load_march(const Pool<NSLOT>& pool, int slot, Ma
     if (VAR::MARCHER != MARCH_PLAIN) {
         m.w = pool.getf(F_W, slot); m.s = pool.getf(F_S, slot); m.d = pool.getf(F_D, slot);
     }
-#if defined(RT_JIT_BBOX)
+#if defined(RT_JIT_TSTOP)
     if (VAR::MARCHER != MARCH_SRC) m.t_stop = pool.getf(F_TSTOP, slot);
 #endif
 }
@@ -113,7 +113,7 @@ __device__ __forceinline__ void store_ready(Pool<NSLOT>& pool, int slot, const M
     pool.setf(F_RDX, slot, m.rd.x); pool.setf(F_RDY, slot, m.rd.y); pool.setf(F_RDZ, slot, m.rd.z);
     pool.setf(F_T, slot, m.t);
     pool.seti(F_STEPS, slot, m.steps);
-#if defined(RT_JIT_BBOX)
+#if defined(RT_JIT_TSTOP)
     if (VAR::MARCHER != MARCH_SRC) pool.setf(F_TSTOP, slot, m.t_stop);
 #endif
     if (VAR::MARCHER != MARCH_PLAIN) {
@@ -159,6 +159,12 @@ __device__ __forceinline__ void zero_march(MarchState& m)
 #define RT_REGEN_MIN 0
 #endif
 enum : int { MODE_ALL = 0, MODE_HITS = 1, MODE_FRESH = 2 };
+#ifndef RT_FIN_MIN
+#define RT_FIN_MIN 1
+#endif
+#ifndef RT_REGEN_IDLE
+#define RT_REGEN_IDLE 1      // regeneration batches also run when at least this many lanes have nothing to march
+#endif
 
 template <class VAR, int NSLOT, int MODE = MODE_ALL>
 __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& pool, const int slot, const int lane,
@@ -327,7 +333,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
             if (begun && ray_is_irregular(p.m)) {
                 st = march_to_end_generic<VAR>(P, p.m) == MARCH_HIT ? ST_HIT : ST_MISS;
             } else if (begun || st == ST_SLOW) {
-#if defined(RT_JIT_BBOX)
+#if defined(RT_JIT_TSTOP)
                 if (begun) p.m.t_stop = ray_t_stop<VAR>(P, p.m);
 #endif
 #if defined(RT_JIT_FAST)
@@ -439,7 +445,12 @@ __device__ __forceinline__ void pool_body(const KParams& P)
 
         // ---------------------------------------------------------------- resolve phase
         int n_wait = n_pend;          // slots the resolve phase could work on
-        if (kRegen && active != kFull) n_wait += (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
+        bool regen = false;           // warp-uniform: regeneration batches run in this round
+        if (kRegen && active != kFull) {
+            const int n_fresh = (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
+            regen = n_fresh > 0 && (n_fresh >= RT_REGEN_MIN || 32 - __popc(active) >= RT_REGEN_IDLE);
+            if (regen) n_wait += n_fresh;
+        }
         if (active != kFull && n_wait > 0 && (n_wait >= P.resolve_min || active == 0u)) {
             if (VAR::COUNT) c_rounds++;
             __syncwarp();    // the acquire above may have read the stack entries that parking overwrites
@@ -477,13 +488,14 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                 // regeneration: when enough slots wait for a new path, or when lanes would idle otherwise
                 for (;;) {
                     const int n_fresh = (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
-                    if (n_fresh == 0 || !(n_fresh >= RT_REGEN_MIN || n_ready < 32)) break;
+                    if (n_fresh == 0 || !(regen || n_fresh >= RT_REGEN_MIN)) break;
                     const int take = min(n_fresh, 32);
                     const int slot = lane < take ? (int)fresh[n_fresh - 1 - lane] : -1;
                     __syncwarp();
                     if (lane == 0) wq[WQ_NFRESH] = (uint32_t)(n_fresh - take);
                     __syncwarp();
                     resolve_batch<VAR, NSLOT, MODE_FRESH>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt, pend, &n_pend, fresh);
+                    regen = false;                                // further batches only while they are well filled
                 }
             }
             continue;
@@ -520,7 +532,19 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             if (fin != 0u) break;
         }
 #else
-#if defined(RT_MARCH_VOTE_EVERY_2)
+#if RT_FIN_MIN > 1
+        // Leaving the march loop costs ~45 warp instructions (store, push, pop, load) however few lanes finished, and
+        // with 32 lanes x ~28 steps per ray some lane finishes on almost every step.  So finished lanes wait (masked)
+        // until RT_FIN_MIN of them can be handled in one go -- or every lane that holds a slot has finished.
+        {
+            const int thr = min(RT_FIN_MIN, __popc(__ballot_sync(kFull, my >= 0)));
+            bool done = false;
+            do {
+                if (!done) done = march_step_fin<VAR>(P, m, aux, slow);
+                fin = __ballot_sync(kFull, done && my >= 0);
+            } while (__popc(fin) < thr);
+        }
+#elif defined(RT_MARCH_VOTE_EVERY_2)
         // tuning knob (RTPBR_MARCH_UNROLL=2): vote after every second step; a lane whose march ends on the first
         // one sits the second one out
         do {

@@ -72,6 +72,9 @@ HC_API int hostcheck_jit_march(const RtpbrConfig* cfg, const RtpbrObject* objs, 
     if (cfg->family == RTPBR_FAMILY_B) return jit_march_check_t<Variant<FAMILY_B, 0, SHAPESET_ANALYTIC, MARCH_ENHANCED, false>>(P, rays, nrays, out);
     return jit_march_check_t<Variant<FAMILY_C, 0, SHAPESET_ANALYTIC, MARCH_SRC, false>>(P, rays, nrays, out);
 }
+#if defined(RT_JIT_STATS)
+HC_API unsigned long long* hostcheck_jit_stats(void) { return g_jit_stats; }
+#endif
 // points x npts: wherever jit_nearest_fast() says ok its result must have the bits of jit_nearest_dist().  Returns the
 // number of violations, -1 when the scene has no fast region; *n_ok = points inside the region.
 HC_API int hostcheck_jit_fast(const RtpbrConfig* cfg, const RtpbrObject* objs, int n, int frame, const float* pts, int npts, int* n_ok)

@@ -172,6 +172,8 @@ def test_specialised_source_carries_the_right_variant_switches():
     for preset in (scenes.tokyo_ibl, scenes.cornell_box, scenes.cornell_box_v3, scenes.src_scene):
         b, _ = src_of(preset)
         assert "#define RT_RESOLVE_OOL 1" in b and "RT_JIT_SPLIT_BUNNY" not in b
+        assert "RT_JIT_FAST" not in b                                    # automatic policy: fast region for family A only
+        assert ("#define RT_JIT_BBOX 1" in b) == (preset is scenes.tokyo_ibl)   # t_stop where the scene has a sky (not src/)
     c, _ = src_of(scenes.bunny_glass)
     assert "#define RT_JIT_SPLIT_BUNNY 1" in c and "RT_RESOLVE_OOL" not in c
     assert "jit_nearest_partial(const KParams& P, vec3 pos, bool& need_mlp, vec3& pb)" in c and "rt_inf()" in c
@@ -182,12 +184,22 @@ _JIT_HC = {}
 
 
 def jit_hostcheck(name, tmp_path_factory):
-    """tests/native/hostcheck.cu compiled together with the scene-specialised translation unit of preset `name`."""
+    """tests/native/hostcheck.cu compiled together with the scene-specialised translation unit of preset `name`, with
+    both analyses forced on wherever they apply (the automatic policy keeps them for the scenes where they pay)."""
     if name in _JIT_HC:
         return _JIT_HC[name]
     preset = PRESETS[name][0]
     cfg, objs, cam, _ = preset(40, 32, seed=5, max_bounces=6)
-    src = N.jit_source(cfg, [o.to_native() for o in objs])
+    old = {k: os.environ.get(k) for k in ("RTPBR_JIT_FAST", "RTPBR_JIT_BBOX")}
+    os.environ.update(RTPBR_JIT_FAST="1", RTPBR_JIT_BBOX="1")
+    try:
+        src = N.jit_source(cfg, [o.to_native() for o in objs])
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     d = tmp_path_factory.mktemp("jit_hc_" + name)
     pre = src[:src.index('#include "pool_kernel.cuh"')]
     body = src[src.index("namespace rt {") + len("namespace rt {"):src.index("}  // namespace rt")]
@@ -312,10 +324,16 @@ def test_specialised_kernel_does_not_depend_on_who_loaded_an_nvrtc_first(tmp_pat
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("forced", [False, True])
 @pytest.mark.parametrize("name", list(PRESETS))
-def test_jit_and_aot_kernels_give_the_same_bits(name):
+def test_jit_and_aot_kernels_give_the_same_bits(name, forced, monkeypatch):
+    """forced: fast region and scene bounds compiled in wherever the analysis permits, not only where the automatic
+    policy keeps them (jit_codegen.h) -- with the regeneration batches and the finish threshold the fast kernels use."""
     from raytracingpbr_b200 import PathTracer
     preset = PRESETS[name][0]
+    if forced:
+        for k, v in dict(RTPBR_JIT_FAST="1", RTPBR_JIT_BBOX="1", RTPBR_REGEN_MIN="16", RTPBR_REGEN_IDLE="8", RTPBR_FIN_MIN="4").items():
+            monkeypatch.setenv(k, v)
     cfg, objs, cam, tm = preset(96, 64, seed=3, max_bounces=8)
     out = {}
     for jit in (True, False):
