@@ -208,11 +208,38 @@ RTPBR_API int rtpbr_nccl_unique_id(void* id128);                       /* 128 by
 RTPBR_API int rtpbr_nccl_init(RtpbrContext* ctx, const void* id128, int rank, int nranks);
 RTPBR_API int rtpbr_reduce_tiles(RtpbrContext* ctx, int root);         /* root < 0: all-reduce */
 
+/* After rtpbr_reduce_tiles the root's (all ranks', for root < 0) image_buffer holds the SUM over ranks: tracing on would
+ * count the other ranks' samples twice at the next reduce, so rtpbr_pathtrace fails with RTPBR_ERR_STATE until
+ * rtpbr_refresh.  A context sharded with rtpbr_set_shard(nranks > 1) that has no communicator fails too. */
+
+/* Single-process multi-GPU (SURVEY.md 8(b) `pt_create_multi`): n contexts, one per device, column bands of `band`
+ * columns interleaved across them (rank = (column / band) mod n), one NCCL communicator per GPU created by the calling
+ * thread.  The setters broadcast; rtpbr_multi_pathtrace queues one asynchronous launch per GPU; rtpbr_multi_post_process
+ * sums the per-GPU sample sums onto rank 0 (the only collective: NCCL at tonemap time) and tone-maps there;
+ * rtpbr_multi_download reads rank 0.  rtpbr_multi_context lends the per-GPU context (timers, counters, jit status). */
+typedef struct RtpbrMulti RtpbrMulti;
+RTPBR_API int rtpbr_multi_create(const RtpbrConfig* cfg, const int* devices, int n, int band, RtpbrMulti** out);
+RTPBR_API int rtpbr_multi_destroy(RtpbrMulti* m);
+RTPBR_API int rtpbr_multi_count(RtpbrMulti* m);
+RTPBR_API RtpbrContext* rtpbr_multi_context(RtpbrMulti* m, int rank);
+RTPBR_API int rtpbr_multi_set_scene(RtpbrMulti* m, const RtpbrObject* objects, int n);
+RTPBR_API int rtpbr_multi_set_camera(RtpbrMulti* m, const RtpbrCamera* cam);
+RTPBR_API int rtpbr_multi_set_envmap(RtpbrMulti* m, const float* rgb, int w, int h);
+RTPBR_API int rtpbr_multi_set_frame(RtpbrMulti* m, int frame);
+RTPBR_API int rtpbr_multi_set_sample_base(RtpbrMulti* m, uint32_t sample_base);
+RTPBR_API int rtpbr_multi_refresh(RtpbrMulti* m);
+RTPBR_API int rtpbr_multi_pathtrace(RtpbrMulti* m, int spp);
+RTPBR_API int rtpbr_multi_reduce(RtpbrMulti* m, int root);
+RTPBR_API int rtpbr_multi_post_process(RtpbrMulti* m, int mode, float exposure, double gamma);
+RTPBR_API int rtpbr_multi_download(RtpbrMulti* m, int which, void* host, size_t bytes);
+RTPBR_API int rtpbr_multi_sync(RtpbrMulti* m);
+
 /* device pointer of a buffer (for zero-copy interop, e.g. __cuda_array_interface__) */
 RTPBR_API int rtpbr_device_ptr(RtpbrContext* ctx, int which, uint64_t* ptr);
 
 RTPBR_API const char* rtpbr_last_error(void);
 RTPBR_API int rtpbr_version(void);
+RTPBR_API int rtpbr_device_count(void);      /* usable CUDA devices (0 without a driver) */
 RTPBR_API int rtpbr_sizeof_config(void);
 RTPBR_API int rtpbr_sizeof_object(void);
 RTPBR_API int rtpbr_sizeof_camera(void);

@@ -34,6 +34,10 @@ EXPORTS = (
     "rtpbr_get_counters", "rtpbr_device_info", "rtpbr_nccl_unique_id", "rtpbr_nccl_init", "rtpbr_reduce_tiles",
     "rtpbr_device_ptr", "rtpbr_set_jit", "rtpbr_jit_status", "rtpbr_jit_generate", "rtpbr_jit_compile_check", "rtpbr_last_error", "rtpbr_version", "rtpbr_sizeof_config", "rtpbr_sizeof_object",
     "rtpbr_sizeof_camera",
+    "rtpbr_multi_create", "rtpbr_multi_destroy", "rtpbr_multi_count", "rtpbr_multi_context", "rtpbr_multi_set_scene",
+    "rtpbr_multi_set_camera", "rtpbr_multi_set_envmap", "rtpbr_multi_set_frame", "rtpbr_multi_set_sample_base",
+    "rtpbr_multi_refresh", "rtpbr_multi_pathtrace", "rtpbr_multi_reduce", "rtpbr_multi_post_process",
+    "rtpbr_multi_download", "rtpbr_multi_sync", "rtpbr_device_count",
 )
 
 
@@ -134,6 +138,21 @@ def lib() -> C.CDLL:
         "rtpbr_jit_status": [vp, C.c_char_p, C.c_size_t],
         "rtpbr_jit_compile_check": [C.POINTER(RtpbrConfig), C.POINTER(RtpbrObject), C.c_int, C.c_char_p, C.c_size_t],
         "rtpbr_version": [], "rtpbr_sizeof_config": [], "rtpbr_sizeof_object": [], "rtpbr_sizeof_camera": [],
+        "rtpbr_device_count": [],
+        "rtpbr_multi_create": [C.POINTER(RtpbrConfig), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)],
+        "rtpbr_multi_destroy": [vp],
+        "rtpbr_multi_count": [vp],
+        "rtpbr_multi_set_scene": [vp, C.POINTER(RtpbrObject), C.c_int],
+        "rtpbr_multi_set_camera": [vp, C.POINTER(RtpbrCamera)],
+        "rtpbr_multi_set_envmap": [vp, C.POINTER(C.c_float), C.c_int, C.c_int],
+        "rtpbr_multi_set_frame": [vp, C.c_int],
+        "rtpbr_multi_set_sample_base": [vp, C.c_uint32],
+        "rtpbr_multi_refresh": [vp],
+        "rtpbr_multi_pathtrace": [vp, C.c_int],
+        "rtpbr_multi_reduce": [vp, C.c_int],
+        "rtpbr_multi_post_process": [vp, C.c_int, C.c_float, C.c_double],
+        "rtpbr_multi_download": [vp, C.c_int, vp, C.c_size_t],
+        "rtpbr_multi_sync": [vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -141,6 +160,8 @@ def lib() -> C.CDLL:
         fn.restype = C.c_int
     L.rtpbr_jit_generate.argtypes = [C.POINTER(RtpbrConfig), C.POINTER(RtpbrObject), C.c_int, C.c_char_p, C.c_size_t]
     L.rtpbr_jit_generate.restype = C.c_longlong
+    L.rtpbr_multi_context.argtypes = [vp, C.c_int]
+    L.rtpbr_multi_context.restype = vp
     L.rtpbr_last_error.argtypes = []
     L.rtpbr_last_error.restype = C.c_char_p
     if L.rtpbr_sizeof_config() != C.sizeof(RtpbrConfig) or L.rtpbr_sizeof_object() != C.sizeof(RtpbrObject) \
@@ -148,6 +169,10 @@ def lib() -> C.CDLL:
         raise ImportError("librtpbr.so struct layout differs from the ctypes mirror: rebuild the library")
     _lib = L
     return L
+
+
+def device_count() -> int:
+    return int(lib().rtpbr_device_count())
 
 
 def check(rc: int) -> None:
@@ -231,19 +256,23 @@ def _find_nccl() -> str | None:
 class Context:
     """Owns one RtpbrContext (one GPU, one stream, all device buffers)."""
 
-    def __init__(self, cfg: RtpbrConfig, device: int = 0):
+    def __init__(self, cfg: RtpbrConfig, device: int = 0, _borrowed=None):
         self._L = lib()
         self.cfg = cfg
         self.width, self.height = cfg.width, cfg.height
+        self._owned = _borrowed is None
+        if _borrowed is not None:          # a context lent by a MultiContext (rtpbr_multi_context)
+            self._h = _borrowed
+            return
         h = C.c_void_p()
         _point_at_nvrtc()
         check(self._L.rtpbr_create(C.byref(cfg), device, C.byref(h)))
         self._h = h
-        self._keep = []
 
     def close(self) -> None:
         if getattr(self, "_h", None):
-            self._L.rtpbr_destroy(self._h)
+            if self._owned:
+                self._L.rtpbr_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -369,3 +398,87 @@ class Context:
 
     def reduce_tiles(self, root: int = 0) -> None:
         check(self._L.rtpbr_reduce_tiles(self._h, root))
+
+
+class MultiContext:
+    """Owns one RtpbrMulti: n GPUs driven by this one process (rtpbr_multi_*, include/rtpbr.h).  No torch, no MPI: the
+    NCCL communicators are created by the library itself."""
+
+    def __init__(self, cfg: RtpbrConfig, devices, band: int = 4):
+        self._L = lib()
+        self.cfg = cfg
+        self.width, self.height = cfg.width, cfg.height
+        devices = list(devices)
+        _point_at_nvrtc()
+        p = _find_nccl()
+        if p and not os.environ.get("RTPBR_NCCL_LIB"):
+            os.environ["RTPBR_NCCL_LIB"] = p
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        check(self._L.rtpbr_multi_create(C.byref(cfg), arr, len(devices), band, C.byref(h)))
+        self._h = h
+        self.devices, self.band = devices, band
+        self.ranks = [Context(cfg, _borrowed=C.c_void_p(self._L.rtpbr_multi_context(h, r))) for r in range(len(devices))]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            for c in self.ranks:
+                c.close()
+            self._L.rtpbr_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_scene(self, objects) -> None:
+        arr = (RtpbrObject * len(objects))(*objects)
+        check(self._L.rtpbr_multi_set_scene(self._h, arr, len(objects)))
+
+    def set_camera(self, cam: RtpbrCamera) -> None:
+        check(self._L.rtpbr_multi_set_camera(self._h, C.byref(cam)))
+
+    def set_envmap(self, rgb: np.ndarray) -> None:
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        assert rgb.ndim == 3 and rgb.shape[2] == 3
+        check(self._L.rtpbr_multi_set_envmap(self._h, rgb.ctypes.data_as(C.POINTER(C.c_float)), rgb.shape[0], rgb.shape[1]))
+
+    def set_frame(self, frame: int) -> None:
+        check(self._L.rtpbr_multi_set_frame(self._h, int(frame)))
+
+    def set_sample_base(self, base: int) -> None:
+        check(self._L.rtpbr_multi_set_sample_base(self._h, int(base)))
+
+    def refresh(self) -> None:
+        check(self._L.rtpbr_multi_refresh(self._h))
+
+    def pathtrace(self, spp: int = 1) -> None:
+        check(self._L.rtpbr_multi_pathtrace(self._h, int(spp)))
+
+    def reduce(self, root: int = 0) -> None:
+        check(self._L.rtpbr_multi_reduce(self._h, root))
+
+    def post_process(self, mode: int, exposure: float = 1.0, gamma: float = 2.2) -> None:
+        check(self._L.rtpbr_multi_post_process(self._h, mode, exposure, gamma))
+
+    def sync(self) -> None:
+        check(self._L.rtpbr_multi_sync(self._h))
+
+    def download(self, which: int = BUF_IMAGE_BUFFER, out: np.ndarray | None = None) -> np.ndarray:
+        ch = {BUF_IMAGE_BUFFER: 4, BUF_IMAGE_PIXELS: 3, BUF_RAY_BUFFER: 10, BUF_DIFF_BUFFER: 2, BUF_DIFF_PIXELS: 1}[which]
+        if out is None:
+            out = np.empty((self.width, self.height, ch), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.width, self.height, ch)
+        check(self._L.rtpbr_multi_download(self._h, which, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def jit_status(self):
+        return self.ranks[0].jit_status()

@@ -42,6 +42,8 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -63,7 +65,10 @@ bool load_nccl(std::string& why)
     g_nccl.Reduce = (decltype(g_nccl.Reduce))dlsym(h, "ncclReduce");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Reduce || !g_nccl.CommDestroy) {
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Reduce || !g_nccl.CommDestroy ||
+        !g_nccl.GroupStart || !g_nccl.GroupEnd) {
         why = "libnccl is missing required symbols";
         return false;
     }
@@ -109,6 +114,7 @@ struct RtpbrContext {
     int jit_churn = 0;            // recent NVRTC compiles (decays per pathtrace): animated scenes fall back to the ahead-of-time kernel
     void* nccl_comm = nullptr;
     int nccl_rank = 0, nccl_nranks = 1;
+    bool holds_reduced = false;   // image_buffer holds the sum over ranks (after rtpbr_reduce_tiles): refresh before tracing on
     unsigned long long launches = 0;
 };
 
@@ -153,6 +159,11 @@ extern "C" {
 
 const char* rtpbr_last_error(void) { return g_last_error.c_str(); }
 int rtpbr_version(void) { return RTPBR_VERSION; }
+int rtpbr_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 int rtpbr_sizeof_config(void) { return (int)sizeof(RtpbrConfig); }
 int rtpbr_sizeof_object(void) { return (int)sizeof(RtpbrObject); }
 int rtpbr_sizeof_camera(void) { return (int)sizeof(RtpbrCamera); }
@@ -353,6 +364,7 @@ int rtpbr_refresh(RtpbrContext* c)
     if (!c) return fail(RTPBR_ERR_ARG, "null context");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemsetAsync(c->d_image_buffer, 0, npixels(c) * sizeof(float4), c->stream));
+    c->holds_reduced = false;
     if (c->d_ray_buffer) CUDA_TRY(rt::launch_refresh_depth(c->d_ray_buffer, (int)npixels(c), c->stream));
     if (c->d_diff_buffer) CUDA_TRY(rt::launch_refresh_adaptive(c->d_diff_buffer, c->d_diff_pixels, (int)npixels(c), c->stream));
     return RTPBR_OK;
@@ -509,6 +521,9 @@ int rtpbr_pathtrace(RtpbrContext* c, int spp)
     if (!c) return fail(RTPBR_ERR_ARG, "null context");
     if (spp < 1) return fail(RTPBR_ERR_ARG, "spp must be >= 1");
     if (!c->have_scene || !c->have_camera) return fail(RTPBR_ERR_STATE, "set_scene and set_camera must precede pathtrace");
+    if (c->holds_reduced)
+        return fail(RTPBR_ERR_STATE, "image_buffer holds the sum over all ranks (rtpbr_reduce_tiles): accumulating this rank's "
+                                     "shard on top of it would count the other ranks twice at the next reduce; call rtpbr_refresh first");
     CUDA_TRY(cudaSetDevice(c->device));
     const rt::KernelSelect sel = select_kernel(c);
     if (c->P.total_work == 0) {  // this rank owns no columns
@@ -831,7 +846,131 @@ int rtpbr_reduce_tiles(RtpbrContext* c, int root)
     else
         r = g_nccl.Reduce(c->d_image_buffer, c->d_image_buffer, count, 7, 0, root, c->nccl_comm, c->stream);
     if (r != 0) return fail(RTPBR_ERR_NCCL, std::string("nccl reduce: ") + g_nccl.GetErrorString(r));
+    if (root < 0 || root == c->nccl_rank) c->holds_reduced = true;
     return RTPBR_OK;
+}
+
+// ------------------------------------------------------------------------------ single-process multi-GPU
+}  // extern "C"
+
+struct RtpbrMulti {
+    std::vector<RtpbrContext*> ctx;
+    int band = 4;
+};
+
+extern "C" {
+
+int rtpbr_multi_create(const RtpbrConfig* cfg, const int* devices, int n, int band, RtpbrMulti** out)
+{
+    if (!cfg || !devices || !out || n < 1 || n > 64 || band < 1) return fail(RTPBR_ERR_ARG, "bad argument");
+    *out = nullptr;
+    for (int a = 0; a < n; ++a)
+        for (int b = a + 1; b < n; ++b)
+            if (devices[a] == devices[b]) return fail(RTPBR_ERR_ARG, "the same device appears twice");
+    std::unique_ptr<RtpbrMulti> m(new (std::nothrow) RtpbrMulti());
+    if (!m) return fail(RTPBR_ERR_ARG, "out of host memory");
+    m->band = band;
+    auto destroy_all = [&]() { for (RtpbrContext* c : m->ctx) rtpbr_destroy(c); m->ctx.clear(); };
+    for (int r = 0; r < n; ++r) {
+        RtpbrContext* c = nullptr;
+        int rc = rtpbr_create(cfg, devices[r], &c);
+        if (rc == RTPBR_OK) rc = rtpbr_set_shard(c, r, n, band);
+        if (rc != RTPBR_OK) { if (c) rtpbr_destroy(c); destroy_all(); return rc; }
+        m->ctx.push_back(c);
+    }
+    if (n > 1) {
+        // one communicator per GPU, created by this one thread: ncclCommInitRank inside a group (= ncclCommInitAll)
+        std::string why;
+        if (!load_nccl(why)) { destroy_all(); return fail(RTPBR_ERR_NCCL, why); }
+        UniqueId id;
+        int r = g_nccl.GetUniqueId(&id);
+        if (r != 0) { destroy_all(); return fail(RTPBR_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r)); }
+        g_nccl.GroupStart();
+        for (int k = 0; k < n && r == 0; ++k) {
+            cudaSetDevice(m->ctx[k]->device);
+            r = g_nccl.CommInitRank(&m->ctx[k]->nccl_comm, n, id, k);
+            m->ctx[k]->nccl_rank = k;
+            m->ctx[k]->nccl_nranks = n;
+        }
+        const int e = g_nccl.GroupEnd();
+        if (r == 0) r = e;
+        if (r != 0) { destroy_all(); return fail(RTPBR_ERR_NCCL, std::string("ncclCommInitRank (group): ") + g_nccl.GetErrorString(r)); }
+    }
+    *out = m.release();
+    return RTPBR_OK;
+}
+
+int rtpbr_multi_destroy(RtpbrMulti* m)
+{
+    if (!m) return RTPBR_OK;
+    for (RtpbrContext* c : m->ctx) rtpbr_destroy(c);
+    delete m;
+    return RTPBR_OK;
+}
+
+int rtpbr_multi_count(RtpbrMulti* m) { return m ? (int)m->ctx.size() : 0; }
+
+RtpbrContext* rtpbr_multi_context(RtpbrMulti* m, int rank)
+{
+    if (!m || rank < 0 || rank >= (int)m->ctx.size()) { fail(RTPBR_ERR_ARG, "bad rank"); return nullptr; }
+    return m->ctx[rank];
+}
+
+#define MULTI_EACH(call)                                                     \
+    do {                                                                     \
+        if (!m) return fail(RTPBR_ERR_ARG, "null argument");                 \
+        for (RtpbrContext* c : m->ctx) {                                     \
+            const int rc__ = (call);                                         \
+            if (rc__ != RTPBR_OK) return rc__;                               \
+        }                                                                    \
+        return RTPBR_OK;                                                     \
+    } while (0)
+
+int rtpbr_multi_set_scene(RtpbrMulti* m, const RtpbrObject* objects, int n) { MULTI_EACH(rtpbr_set_scene(c, objects, n)); }
+int rtpbr_multi_set_camera(RtpbrMulti* m, const RtpbrCamera* cam) { MULTI_EACH(rtpbr_set_camera(c, cam)); }
+int rtpbr_multi_set_envmap(RtpbrMulti* m, const float* rgb, int w, int h) { MULTI_EACH(rtpbr_set_envmap(c, rgb, w, h)); }
+int rtpbr_multi_set_frame(RtpbrMulti* m, int frame) { MULTI_EACH(rtpbr_set_frame(c, frame)); }
+int rtpbr_multi_set_sample_base(RtpbrMulti* m, uint32_t base) { MULTI_EACH(rtpbr_set_sample_base(c, base)); }
+int rtpbr_multi_refresh(RtpbrMulti* m) { MULTI_EACH(rtpbr_refresh(c)); }
+// launches are asynchronous: the loop queues one kernel per GPU and they run side by side
+int rtpbr_multi_pathtrace(RtpbrMulti* m, int spp) { MULTI_EACH(rtpbr_pathtrace(c, spp)); }
+int rtpbr_multi_sync(RtpbrMulti* m) { MULTI_EACH(rtpbr_sync(c)); }
+#undef MULTI_EACH
+
+int rtpbr_multi_reduce(RtpbrMulti* m, int root)
+{
+    if (!m) return fail(RTPBR_ERR_ARG, "null argument");
+    if (root >= (int)m->ctx.size()) return fail(RTPBR_ERR_ARG, "bad root");
+    if (m->ctx.size() == 1) return RTPBR_OK;
+    g_nccl.GroupStart();
+    int rc = RTPBR_OK;
+    for (RtpbrContext* c : m->ctx) {
+        rc = rtpbr_reduce_tiles(c, root);
+        if (rc != RTPBR_OK) break;
+    }
+    const int e = g_nccl.GroupEnd();
+    if (rc != RTPBR_OK) return rc;
+    if (e != 0) return fail(RTPBR_ERR_NCCL, std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(e));
+    return RTPBR_OK;
+}
+
+int rtpbr_multi_post_process(RtpbrMulti* m, int mode, float exposure, double gamma)
+{
+    if (!m) return fail(RTPBR_ERR_ARG, "null argument");
+    if (m->ctx[0]->cfg.family == RTPBR_FAMILY_C && m->ctx.size() > 1 && !m->ctx[0]->holds_reduced)
+        return fail(RTPBR_ERR_UNSUPPORTED, "family C keeps per-pixel ray state between launches: reduce explicitly "
+                                           "(rtpbr_multi_reduce) when the frame is finished, then post_process");
+    if (m->ctx.size() > 1 && !m->ctx[0]->holds_reduced) {
+        const int rc = rtpbr_multi_reduce(m, 0);
+        if (rc != RTPBR_OK) return rc;
+    }
+    return rtpbr_post_process(m->ctx[0], mode, exposure, gamma);
+}
+
+int rtpbr_multi_download(RtpbrMulti* m, int which, void* host, size_t bytes)
+{
+    if (!m) return fail(RTPBR_ERR_ARG, "null argument");
+    return rtpbr_download(m->ctx[0], which, host, bytes);
 }
 
 }  // extern "C"

@@ -191,11 +191,15 @@ template <class VAR>
 static cudaError_t launch_pool_t(const KParams& P, int grid, cudaStream_t stream)
 {
     constexpr size_t smem = pool_smem_bytes<kPoolSlots>();
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_pathtrace_pool<VAR, kPoolSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the attribute is per device: remember which devices this instantiation has been configured on
+    static unsigned long long configured = 0ull;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 64 || !((configured >> dev) & 1ull)) {
+        e = cudaFuncSetAttribute(k_pathtrace_pool<VAR, kPoolSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev < 64) configured |= 1ull << dev;
     }
     k_pathtrace_pool<VAR, kPoolSlots><<<grid, kPoolBlock, smem, stream>>>(P);
     return cudaGetLastError();

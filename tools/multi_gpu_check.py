@@ -22,16 +22,16 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 W, H, SPP, B = 320, 192, 6, 8
 cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=B, seed=5)
 with PathTracer(cfg, objs, cam, tm, device=local) as pt:
-    pt.ctx.set_shard(rank, world, 32)
+    pt.set_shard(rank, world, 32)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         uid = torch.frombuffer(bytearray(N.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
     dist.broadcast(uid, 0)
-    pt.ctx.nccl_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    pt.nccl_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
     pt.refresh()
     pt.pathtrace(SPP)
     own = pt.image_buffer.to_numpy()
-    pt.ctx.reduce_tiles(0)
+    pt.reduce_tiles(0)
     pt.post_process()
     img = pt.image_buffer.to_numpy()
 mine = ((np.arange(W) // 32) % world) == rank
