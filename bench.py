@@ -1,40 +1,48 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the path-tracing hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4]
 
-Workload (config.workload): C1 of BASELINE.md -- Cornell Box of
-examples/cornell_box/cornell_box_shortest.py, 1024 x 1024, 64 spp, max 8 bounces.  One "step" =
-one pass of the hot path over that batch: refresh() + pathtrace(spp) (+ the NCCL tile reduce
-when N > 1).  Metric: Msamples/s = pixels x spp / seconds.
+Headline workload (config.workload): C1 of BASELINE.md -- Cornell Box of examples/cornell_box/cornell_box_shortest.py,
+1024 x 1024, 64 spp, max 8 bounces.  One "step" = one pass of the hot path over that batch: refresh() + pathtrace(spp)
+(+ the NCCL tile reduce when N > 1).  Metric: Msamples/s = pixels x spp / seconds.
 
-N > 1 (launched by torchrun, one process per GPU): the image is sharded by 4-column bands
-(rank = (i / 4) mod N) and the spp is scaled by N, so every GPU traces the same number of
-samples as at N = 1 (weak scaling); the only collective is the NCCL sum of per-tile sample
-sums at the end of the step (tonemap time).  torch.distributed is used for the barrier, the
-max-over-ranks reduction of the timings and the NCCL-id broadcast only.
+N > 1 (launched by torchrun, one process per GPU): the image is sharded by 4-column bands (rank = (i / 4) mod N); the only
+collective is the NCCL sum of per-tile sample sums at the end of the step (tonemap time).  torch.distributed is used for
+the barrier, the max-over-ranks reduction of the timings and the NCCL-id broadcast only; the render goes through
+raytracingpbr_b200.PathTracer (set_shard / nccl_init / reduce_tiles).
 
-Legs
-  value         device-resident: scene, camera and accumulation buffer already in HBM.
-  e2e           the same step through the public Python API (raytracingpbr_b200.PathTracer) with
-                HOST buffers: scene + camera structs copied host->device and the accumulation
-                buffer copied device->host inside the timed region, every step.
-  roofline      dominant kernel (k_pathtrace_pool) timed with CUDA events on its launch
-                stream: algorithmic HBM bytes / duration against MEASURED_PEAKS.json, plus the
-                counted-work FP32 figure that actually bounds this path.
-  cpu_baseline  the CPU oracle (oracle/oracle.c; stand-in for "Taichi ti.cpu", which cannot be
-                installed here) on a bounded sample of the same workload, all host threads.
+What one JSON line carries
+  value / ms_per_step  device-resident WEAK-scaling figure: the spp is scaled by N, so every GPU traces as many samples as at N = 1.
+  e2e           the same step through the public Python API with HOST buffers: scene + camera structs copied
+                host->device and the accumulation buffer copied device->host inside the timed region, every step.
+  strong        BASELINE's multi-GPU case at the C1 size: the FIXED 1024^2 x 64 spp job split over the N ranks -- ms per
+                step, Msamples/s, per-rank kernel ms, the tile reduce alone, and image_crc32 of the reduced accumulation
+                buffer, which must be the same number at N = 1, 2, 4, 8 (the image does not depend on the GPU count).
+  c4            BASELINE configs[4]: 4096^2 x 1024 spp, 8 bounces, tile-sharded over the N ranks (strong); one timed step.
+  workloads     (N = 1) configs[2] (bunny_sdf_glass 1024^2 x 256 spp x 16 bounces) and configs[3] (tokyo_ibl 1920 x 1080 x
+                128 spp x 8 bounces): Msamples/s, kernel ms and the counted-work fraction of the FP32 peak.
+  roofline      the roof that bounds this path: FP32 instruction issue.  achieved = ALGORITHMIC flops (SURVEY.md 8(d):
+                41 flop per box SDF etc. x the reference algorithm's evaluation counts, counted by the counting twin of
+                the kernel) / the kernel's average launch duration (CUDA events on its launch stream).
+  roofline_hbm  the HBM view north_star asks for: 8(d)'s algorithmic bytes (16 B per pixel per launch) and the design's
+                own bytes (16 B per sample of ordered-accumulation scratch) against MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (oracle/oracle.c; stand-in for "Taichi ti.cpu", which cannot be installed here) on a
+                bounded sample of the same workload, all host threads.
   --impl reference   the same CPU oracle as the reference arm (kind "port").
 """
 from __future__ import annotations
 
 import argparse
+import csv
+import glob
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -47,14 +55,13 @@ UNIT = "Msamples/s"
 W, H, SPP, BOUNCES = 1024, 1024, 64, 8
 WORKLOAD = "C1: cornell_box_shortest scene, 1024x1024, 64 spp, max 8 bounces"
 BAND = 4                                 # N > 1: rank = (column / BAND) mod N -- fine interleave balances the ranks
-# bytes / flops per unit
-BYTES_PER_SAMPLE = 16                    # pool kernel: one float4 (radiance, 1) per sample into the scratch buffer
-BYTES_PER_PIXEL_PER_LAUNCH = 32          # simple kernel: vec4 f32 accumulator, 16 B read + 16 B write
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_pathtrace_pool_jit launch at the C1 configuration
-# (ncu --set full, profiles/r01h_ncu_full_k_pathtrace_pool_jit_c1.csv: 102.34 MB read + 1182.56 MB written)
-NCU_TRAFFIC_BYTES_C1 = 102.339072e6 + 1.182560e9
-FLOP_PER_SCENE_EVAL = 8 * 41             # 8 boxes x 41 flop
-FLOP_PER_NORMAL = 4 * 41
+# bytes per unit
+ALG_BYTES_PER_PIXEL_PER_LAUNCH = 16      # 8(d): with the spp loop inside the kernel, one vec4 f32 accumulator per pixel per launch
+DESIGN_BYTES_PER_SAMPLE = 16             # this design: one float4 (radiance, 1) per sample into the ordered-accumulation scratch
+# flops per unit (translate 3 + rotate 15 + primitive; sqrt = 1)
+FLOP_BOX, FLOP_SPHERE, FLOP_CYLINDER = 41, 28, 39
+FLOP_BUNNY_OUTER = 3 + 15 + 15 + 1 + 6 + 2          # translate, rotate, animation matrix + bob, length, compare / subtract
+FLOP_BUNNY_MLP = 1250 + 48 * 20                     # 8(d): ~1.25 kflop + 48 sin; a sine = 3-term reduction + two degree-7/8 polynomials ~ 20 flop
 FLOP_PER_RAY_SHADE = 150
 
 
@@ -65,6 +72,25 @@ def peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def ncu_summary(tag: str):
+    """Metrics of the tracked ncu capture profiles/r02*_ncu_full_*<tag>*.csv (tools/ncu_summary.py output), newest first.
+    Returns ({metric: float}, file name) or ({}, None): the figures that cannot be measured inside a bench run (DRAM
+    bytes, issue-active) are READ from the committed capture and the file is named next to them."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r02*_ncu_full_*{tag}*.csv")), reverse=True)
+    for path in files:
+        out = {}
+        with open(path) as f:
+            for row in csv.reader(f):
+                if len(row) >= 3:
+                    try:
+                        out[row[0]] = float(row[2])
+                    except ValueError:
+                        pass
+        if out:
+            return out, os.path.relpath(path, ROOT)
+    return {}, None
 
 
 class ClockSampler:
@@ -169,22 +195,29 @@ def reference_arm(args, rank: int) -> int:
     spp = CPU_SPP
     for _ in range(args.warmup):
         run_cpu_oracle(1, hoisted=False, bands=4)
-    vals, t_total, n_total = [], 0.0, 0
+    t_total, n_total = 0.0, 0
     for _ in range(args.steps):
         v, n, dt = run_cpu_oracle(spp, hoisted=False)
-        vals.append(v)
         t_total += dt
         n_total += n
     value = n_total / t_total / 1e6
-    sample = (f"{CPU_BANDS * CPU_COLS} of 1024 columns ({CPU_BANDS} spread bands x {CPU_COLS}) x 1024 rows x {spp} spp = "
+    v_h, n_h, dt_h = run_cpu_oracle(spp, hoisted=True)
+    ncols = CPU_BANDS * CPU_COLS
+    sample = (f"{ncols} of {W} columns ({CPU_BANDS} spread bands x {CPU_COLS}) x {H} rows x {spp} spp = "
               f"{n_total // args.steps} samples per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle port of cornell_box_shortest.py (as-written rotation "
-                   "recompute), stand-in for Taichi ti.cpu which is not installable here"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "width": W, "height": H, "spp_per_step": spp, "max_bounces": BOUNCES,
+                   "subsample": {"columns": ncols, "of_columns": W, "rows": H, "spp": spp, "samples_per_step": n_total // args.steps,
+                                 "why": "the CPU path needs ~4 minutes for the whole 67.1 M-sample step; pixels are independent and "
+                                        "the columns are spread over the image, so Msamples/s of the subsample is that of the step"},
+                   "note": "CPU oracle port of cornell_box_shortest.py run as written (rotation matrices recomputed per object per "
+                           "march step, :43), all host threads: the stand-in for Taichi ti.cpu, which is not installable here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "hoisted_value": v_h, "hoisted_note": "same port with the rotation matrices precomputed (the fair algorithmic "
+                                                               f"baseline): {n_h} samples in {dt_h:.1f} s"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,11 +225,184 @@ def reference_arm(args, rank: int) -> int:
     return 0
 
 
-# ------------------------------------------------------------------------------ other configs (informational)
+# ------------------------------------------------------------------------------ torch.distributed plumbing (N > 1 only)
+class Ranks:
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist, self.torch = dist, torch
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _reduce(self, x: float, op):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.MAX if self.dist else None)
+
+    def gather(self, x: float):
+        if self.dist is None:
+            return [x]
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(v.item()) for v in out]
+
+    def broadcast_bytes(self, payload: bytes | None, n: int) -> bytes:
+        if self.dist is None:
+            return payload
+        t = self.torch.zeros(n, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            t = self.torch.frombuffer(bytearray(payload), dtype=self.torch.uint8).cuda()
+        self.dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def sharded_tracer(R: Ranks, width: int, height: int, kernel: int):
+    """PathTracer of this rank for the Cornell scene at (width, height): shard + communicator through the product API."""
+    from raytracingpbr_b200 import PathTracer, nccl_unique_id, scenes
+    cfg, objs, cam, tm = scenes.cornell_box_shortest(width, height, max_bounces=BOUNCES, seed=0, kernel=kernel)
+    pt = PathTracer(cfg, objs, cam, tm, device=R.local)
+    if R.world > 1:
+        pt.set_shard(R.rank, R.world, BAND)
+        uid = R.broadcast_bytes(nccl_unique_id() if R.rank == 0 else None, 128)
+        pt.nccl_init(uid, R.rank, R.world)
+    return pt, objs, cam, tm
+
+
+def timed_steps(R: Ranks, pt, spp: int, warmup: int, steps: int, sampler=None):
+    """`warmup` untimed + `steps` timed device-resident steps (L2 flushed, refresh, pathtrace, tile reduce): barrier +
+    synchronize on both sides, CUDA events on the launch stream, max over ranks.  Returns a dict."""
+    ctx = pt.ctx
+
+    def step():
+        ctx.flush_l2()
+        pt.refresh()
+        ctx.set_sample_base(0)
+        pt.pathtrace(spp)
+        if R.world > 1:
+            pt.reduce_tiles(0)
+    for _ in range(warmup):
+        step()
+    ctx.sync()
+    ctx.kernel_time()                      # reset the per-launch event pool
+    l0 = ctx.counters()["launches"]
+    R.barrier()
+    ctx.sync()
+    if sampler:
+        sampler.start()
+    ctx.timer_start()
+    for _ in range(steps):
+        step()
+    ms = ctx.timer_stop()                  # synchronises the stream
+    R.barrier()
+    clocks = sampler.stop() if sampler else None
+    kernel_ms, kernel_launches = ctx.kernel_time()
+    launches = ctx.counters()["launches"] - l0
+    per_launch = kernel_ms / max(kernel_launches, 1)
+    return {"ms_per_step": R.max(ms) / steps, "kernel_ms_per_step_max": R.max(kernel_ms) / steps, "kernel_launches": kernel_launches,
+            "kernel_ms_per_launch_by_rank": R.gather(per_launch), "launches": launches, "clocks": clocks}
+
+
+def reduce_alone_ms(R: Ranks, pt, spp: int, reps: int = 3) -> float | None:
+    """The NCCL tile reduce by itself: every rank finishes its kernel first (sync + barrier), then CUDA events around
+    rtpbr_reduce_tiles; max over ranks, mean over reps."""
+    if R.world == 1:
+        return None
+    ctx, tot = pt.ctx, 0.0
+    for _ in range(reps):
+        pt.refresh()
+        ctx.set_sample_base(0)
+        pt.pathtrace(min(spp, 4))
+        ctx.sync()
+        R.barrier()
+        ctx.timer_start()
+        pt.reduce_tiles(0)
+        tot += R.max(ctx.timer_stop())
+    return tot / reps
+
+
+def image_crc(R: Ranks, pt, spp: int):
+    """crc32 of the reduced accumulation buffer (rank 0), after one fresh pass; and its alpha sum (= pixels x spp)."""
+    from raytracingpbr_b200 import _native as N
+    ctx = pt.ctx
+    pt.refresh()
+    ctx.set_sample_base(0)
+    pt.pathtrace(spp)
+    if R.world > 1:
+        pt.reduce_tiles(0)
+    crc, alpha = None, None
+    if R.rank == 0:
+        img = ctx.download(N.BUF_IMAGE_BUFFER)
+        crc = zlib.crc32(img.tobytes()) & 0xFFFFFFFF
+        alpha = float(img[..., 3].astype(np.float64).sum())
+    else:
+        ctx.sync()
+    pt.refresh()
+    return crc, alpha
+
+
+# ------------------------------------------------------------------------------ counted work -> FP32 roofline
+def scene_eval_flops(objs) -> int:
+    """Algorithmic flops of ONE scene evaluation (SURVEY.md 8(d) convention), the neural bunny counted by its cheap
+    outer branch (its MLP evaluations are counted separately)."""
+    from raytracingpbr_b200 import scenes
+    per = {scenes.SHAPE_BOX: FLOP_BOX, scenes.SHAPE_SPHERE: FLOP_SPHERE, scenes.SHAPE_CYLINDER: FLOP_CYLINDER,
+           scenes.SHAPE_BUNNY: FLOP_BUNNY_OUTER}
+    return sum(per.get(o.type, FLOP_BOX) for o in objs)                      # (8(d)'s per-primitive figures include the min / argmin step)
+
+
+def counted_work(preset: str, width: int, height: int, bounces: int, spp: int, device: int, env=None):
+    """Untimed pass with the counting twin of the kernel (ahead-of-time, the reference's evaluation sequence)."""
+    from raytracingpbr_b200 import PathTracer, scenes
+    cfg, objs, cam, tm = getattr(scenes, preset)(width, height, max_bounces=bounces, seed=0, count_work=True)
+    with PathTracer(cfg, objs, cam, tm, device=device) as cpt:
+        if env is not None:
+            cpt.set_envmap(env)
+        cpt.refresh()
+        cpt.pathtrace(spp)
+        cpt.sync()
+        c = cpt.ctx.counters()
+    n = max(c["samples"], 1)
+    per = {k: c[k] / n for k in ("scene_evals", "rays", "normals", "mlp_evals")}
+    box_like = scene_eval_flops(objs)
+    flop = (per["scene_evals"] * box_like + per["normals"] * 4 * (box_like / max(len(objs), 1)) + per["rays"] * FLOP_PER_RAY_SHADE
+            + per["mlp_evals"] * FLOP_BUNNY_MLP)
+    lane = (c["march_active"] / c["march_iters"]) if c["march_iters"] else None
+    return per, flop, lane, box_like
+
+
+def fp32_roof(flop_per_sample: float, samples_per_launch: float, kernel_ms_per_launch: float, sm_count: int, sm_max_mhz: float):
+    peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    achieved = flop_per_sample * samples_per_launch / (kernel_ms_per_launch * 1e-3) / 1e12
+    return achieved, peak
+
+
+# ------------------------------------------------------------------------------ other configs
 EXTRA_WORKLOADS = {
-    # name: (preset, width, height, spp, max bounces, (exposure, gamma) of the synthetic environment, description)
-    "c2": ("bunny_glass", 1024, 1024, 256, 16, (1.8, 2.2), "C2: bunny_sdf_glass scene, frame 0, 1024x1024, 256 spp, max 16 bounces"),
-    "c3": ("tokyo_ibl", 1920, 1080, 128, 8, (1.8, 2.2), "C3: tokyo_ibl scene, 1920x1080, 128 spp, max 8 bounces"),
+    # name: (preset, width, height, spp, max bounces, (exposure, gamma), asset file, description)
+    "c2": ("bunny_glass", 1024, 1024, 256, 16, (1.8, 2.2), "limpopo_golf_course_3k.hdr",
+           "C2: bunny_sdf_glass scene, frame 0, 1024x1024, 256 spp, max 16 bounces"),
+    "c3": ("tokyo_ibl", 1920, 1080, 128, 8, (1.8, 2.2), "Tokyo_BigSight_3k.hdr",
+           "C3: tokyo_ibl scene, 1920x1080, 128 spp, max 8 bounces"),
 }
 
 
@@ -213,39 +419,99 @@ def synthetic_env_u8(w=3200, h=1600, seed=11):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def extra_workload(args) -> int:
-    """Single-GPU timing of another BASELINE.json config (no CPU leg, no counters); one JSON line."""
-    from raytracingpbr_b200 import PathTracer, ibl, scenes
-    preset, w, h, spp, bounces, env, desc = EXTRA_WORKLOADS[args.workload]
+def environment(asset: str, exposure: float, gamma: float):
+    """(processed table, description): the real .hdr when $RTPBR_ASSETS holds it, else the procedural stand-in."""
+    from raytracingpbr_b200 import ibl
+    d = os.environ.get("RTPBR_ASSETS")
+    if d and os.path.exists(os.path.join(d, asset)):
+        return ibl.process(ibl.imread(os.path.join(d, asset)), exposure, gamma), f"real asset {asset} ($RTPBR_ASSETS)"
+    return ibl.process(synthetic_env_u8(), exposure, gamma), "synthetic (procedural 3200x1600 environment; set $RTPBR_ASSETS for the .hdr)"
+
+
+def run_extra(name: str, steps: int, warmup: int, device: int = 0, sm_max_mhz: float = 1965.0, with_clocks: bool = False) -> dict:
+    """One of BASELINE configs[2] / configs[3] on one GPU: timing + counted-work fraction of the FP32 peak."""
+    from raytracingpbr_b200 import PathTracer, scenes
+    preset, w, h, spp, bounces, (exposure, gamma), asset, desc = EXTRA_WORKLOADS[name]
+    env, env_desc = environment(asset, exposure, gamma)
     cfg, objs, cam, tm = getattr(scenes, preset)(w, h, max_bounces=bounces, seed=0)
-    with PathTracer(cfg, objs, cam, tm) as pt:
-        pt.set_envmap(ibl.process(synthetic_env_u8(), *env))
+    with PathTracer(cfg, objs, cam, tm, device=device) as pt:
+        pt.set_envmap(env)
         ctx = pt.ctx
 
         def step():
             ctx.flush_l2()
-            ctx.refresh()
+            pt.refresh()
             ctx.set_sample_base(0)
-            ctx.pathtrace(spp)
-        for _ in range(args.warmup):
+            pt.pathtrace(spp)
+        for _ in range(warmup):
             step()
         ctx.sync()
         ctx.kernel_time()
-        sampler = ClockSampler(0)
-        sampler.start()
+        sampler = ClockSampler(device) if with_clocks else None
+        if sampler:
+            sampler.start()
         ctx.timer_start()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         ms = ctx.timer_stop()
-        clocks = sampler.stop()
+        clocks = sampler.stop() if sampler else None
         kernel_ms, launches = ctx.kernel_time()
-        active, jit = ctx.jit_status()
-    line = {"metric": "Msamples/s (pixels x spp / s)", "value": w * h * spp / (ms / args.steps * 1e-3) / 1e6, "unit": UNIT,
-            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (procedural 3200x1600 environment)",
-            "config": {"workload": desc, "jit": jit}, "kernel_ms_per_step": kernel_ms / args.steps, "clocks": clocks}
+        info = ctx.device_info()
+        jit = ctx.jit_status()[1]
+    small = 4 if name == "c2" else 2                       # counting pass at 1/4 (1/2) of the resolution: per-sample work
+    per, flop, lane, eval_flops = counted_work(preset, w // small, h // small, bounces, 2, device, env)
+    k_ms = kernel_ms / max(launches, 1)
+    achieved, peak = fp32_roof(flop, w * h * spp * steps / max(launches, 1), k_ms, info["sm_count"], sm_max_mhz)
+    prof, prof_file = ncu_summary(name)
+    out = {"workload": desc, "value": w * h * spp / (ms / steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "warmup": warmup, "kernel_ms_per_step": kernel_ms / steps, "kernel_launches_per_step": launches / steps, "environment": env_desc,
+           "jit": jit, "blocks_per_sm": info["blocks_per_sm"],
+           "roofline": {"bound": "fp32-issue", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                        "flop_per_sample": flop, "flop_per_scene_eval": eval_flops, "per_sample": per,
+                        "counted_on": f"{w // small}x{h // small} x 2 spp, counting twin (ahead-of-time kernel, the reference's evaluation sequence)",
+                        "issue_active_pct": prof.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "threads_per_instruction": prof.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                        "ncu_source": prof_file}}
+    if clocks:
+        out["clocks"] = clocks
+    return out
+
+
+def extra_workload(args) -> int:
+    """--workload c2 | c3: one JSON line for that configuration alone."""
+    _, _, sm_max = peaks()
+    b = run_extra(args.workload, args.steps, args.warmup, sm_max_mhz=sm_max, with_clocks=True)
+    line = {"metric": "Msamples/s (pixels x spp / s)", "value": b["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": b["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": b["environment"], "config": {"workload": b["workload"], "jit": b["jit"]},
+            "kernel_ms_per_step": b["kernel_ms_per_step"], "clocks": b.get("clocks"), "roofline": b["roofline"]}
     print(json.dumps(line), flush=True)
     return 0
+
+
+def strong_job(R: Ranks, width: int, height: int, spp: int, warmup: int, steps: int, kernel: int, desc: str) -> dict | None:
+    """A FIXED width x height x spp job split over the ranks (BASELINE's multi-GPU case).  Rank 0 gets the dict."""
+    pt, objs, cam, tm = sharded_tracer(R, width, height, kernel)
+    try:
+        t = timed_steps(R, pt, spp, warmup, steps)
+        red = reduce_alone_ms(R, pt, spp)
+        if width * height * spp <= (1 << 28):
+            crc, alpha = image_crc(R, pt, spp)
+            crc_note = f"crc of the reduced {spp} spp accumulation buffer"
+        else:                                            # big jobs: the CRC of a 2-spp pass of the same sharded pipeline
+            crc, alpha = image_crc(R, pt, 2)
+            crc_note = "crc of a 2 spp pass (same sharding, same reduce)"
+    finally:
+        pt.close()
+    if R.rank != 0:
+        return None
+    total = float(width) * height * spp
+    return {"workload": desc, "n_gpus": R.world, "scaling": "strong", "width": width, "height": height, "spp": spp, "steps": steps,
+            "warmup": warmup, "ms_per_step": t["ms_per_step"], "value": total / (t["ms_per_step"] * 1e-3) / 1e6, "unit": UNIT,
+            "kernel_ms_per_step_by_rank": [k * t["kernel_launches"] / steps for k in t["kernel_ms_per_launch_by_rank"]],
+            "kernel_launches_per_step": t["kernel_launches"] / steps,
+            "reduce_tiles_ms": red, "image_crc32": crc, "crc_note": crc_note, "alpha_checksum": alpha,
+            "sharding": f"{R.world} ranks, {BAND}-column interleaved bands" if R.world > 1 else "none"}
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -256,111 +522,46 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-blocks", action="store_true", help="headline only: skip the strong / c4 / workloads blocks")
     ap.add_argument("--kernel", default="persistent", choices=["persistent", "simple"])
-    ap.add_argument("--counters", action="store_true", help="extra untimed pass with work counters (default at N=1)")
     ap.add_argument("--workload", default="c1", choices=list(EXTRA_WORKLOADS) + ["c1", "c4"],
-                    help="c1 = the headline (default); c2 / c3 = BASELINE.json configs[2] / configs[3], informational; "
-                         "c4 = configs[4]: 4096 x 4096 x 1024 spp tile-sharded over the ranks (strong scaling, run under torchrun)")
+                    help="c1 = the headline (default) with its strong / c4 / workloads blocks; c2 / c3 = BASELINE.json configs[2] / "
+                         "configs[3] alone; c4 = configs[4] alone: 4096 x 4096 x 1024 spp tile-sharded over the ranks (strong scaling)")
     args = ap.parse_args()
-    if args.workload in EXTRA_WORKLOADS:
-        return extra_workload(args)
-    global W, H, SPP, WORKLOAD
-    strong = args.workload == "c4"
-    if strong:
-        W, H, SPP = 4096, 4096, 1024
-        WORKLOAD = "C4: cornell_box_shortest scene, 4096x4096, 1024 spp, max 8 bounces, tile-sharded"
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        return reference_arm(args, rank)
+        return reference_arm(args, int(os.environ.get("RANK", "0")))
+    if args.workload in EXTRA_WORKLOADS:
+        return extra_workload(args)
 
-    from raytracingpbr_b200 import PathTracer, _native as N, scenes
-
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # weak scaling (c1): per-GPU samples fixed (W*H*SPP), tiles sharded by column band; c4: the job is fixed
-    spp = SPP if strong else SPP * world
+    from raytracingpbr_b200 import _native as N
+    R = Ranks()
+    rank, world = R.rank, R.world
     kernel = N.KERNEL_PERSISTENT if args.kernel == "persistent" else N.KERNEL_SIMPLE
-    cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=BOUNCES, seed=0, kernel=kernel)
-    pt = PathTracer(cfg, objs, cam, tm, device=local_rank)
-    ctx = pt.ctx
-    if world > 1:
-        import torch
-        ctx.set_shard(rank, world, BAND)
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    hbm_peak, peak_src, sm_max_mhz = peaks()
+
+    if args.workload == "c4":              # configs[4] alone, as the line's headline (strong)
+        blk = strong_job(R, 4096, 4096, 1024, 1, max(1, min(args.steps, 2)), kernel,
+                         "C4: cornell_box_shortest scene, 4096x4096, 1024 spp, max 8 bounces, tile-sharded")
         if rank == 0:
-            uid = torch.frombuffer(bytearray(N.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(uid, 0)
-        ctx.nccl_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+            line = {"metric": METRIC.replace("1024^2", "4096^2"), "value": blk["value"], "unit": UNIT, "n_gpus": world, "steps": blk["steps"],
+                    "warmup": blk["warmup"], "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": blk["workload"], "sharding": blk["sharding"]},
+                    "c4": blk}
+            print(json.dumps(line), flush=True)
+        R.close()
+        return 0
 
-    def step_device():
-        ctx.flush_l2()
-        ctx.refresh()
-        ctx.set_sample_base(0)
-        ctx.pathtrace(spp)
-        if world > 1:
-            ctx.reduce_tiles(0)
-
-    # ---- leg 1: device-resident -----------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    ctx.sync()
-    ctx.kernel_time()                      # reset per-launch event pool
-    l0 = ctx.counters()["launches"]
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    ctx.sync()
-    if sampler:
-        sampler.start()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        step_device()
-    ms = ctx.timer_stop()                  # synchronises the stream
-    barrier()
-    if sampler:
-        clocks = sampler.stop()
-    kernel_ms, kernel_launches = ctx.kernel_time()
-    launches = ctx.counters()["launches"] - l0
-    per_rank_kernel_ms = [kernel_ms / max(kernel_launches, 1)]
-    if dist is not None:
-        import torch
-        t = torch.tensor([kernel_ms / max(kernel_launches, 1)], dtype=torch.float64, device="cuda")
-        out = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        per_rank_kernel_ms = [float(x.item()) for x in out]
-    ms = max_over_ranks(ms)
-    kernel_ms_max = max_over_ranks(kernel_ms)
+    # ---- leg 1: device-resident, weak scaling: per-GPU samples fixed (W*H*SPP), tiles sharded by column band --------
+    spp = SPP * world
+    pt, objs, cam, tm = sharded_tracer(R, W, H, kernel)
+    ctx = pt.ctx
+    sampler = ClockSampler(R.local) if rank == 0 else None
+    t = timed_steps(R, pt, spp, args.warmup, args.steps, sampler)
+    clocks = t["clocks"]
+    ms_per_step = t["ms_per_step"]
     total_samples = float(W) * H * spp     # whole job, all ranks (each rank: W*H*SPP)
-    ms_per_step = ms / args.steps
     value = total_samples / (ms_per_step * 1e-3) / 1e6
 
     # ---- leg 2: end to end through the public API with host buffers --------------------
@@ -377,66 +578,96 @@ def main() -> int:
         ctx.set_sample_base(0)
         pt.pathtrace(spp)
         if world > 1:
-            ctx.reduce_tiles(0)
+            pt.reduce_tiles(0)
         if rank == 0:
             ctx.download(N.BUF_IMAGE_BUFFER, host_img)     # device -> host, synchronises
         else:
             ctx.sync()
 
     step_e2e()
-    barrier()
+    R.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     ctx.sync()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    R.barrier()
+    e2e_s = R.max(time.perf_counter() - t0)
     e2e_value = total_samples * args.steps / e2e_s / 1e6
-    checksum = float(host_img[..., 3].sum()) if rank == 0 else 0.0
+    checksum = float(host_img[..., 3].astype(np.float64).sum()) if rank == 0 else 0.0
+    weak_crc = (zlib.crc32(host_img.tobytes()) & 0xFFFFFFFF) if rank == 0 else None
     host_img = None
     pinned.free()
-
-    # ---- roofline of the dominant kernel ---------------------------------------------
     info = ctx.device_info()
-    hbm_peak, peak_src, sm_max_mhz = peaks()
-    k_ms = kernel_ms_max / max(kernel_launches, 1)
-    local_pixels = W * H / world
-    alg_bytes = (BYTES_PER_SAMPLE * local_pixels * spp if kernel == N.KERNEL_PERSISTENT
-                 else BYTES_PER_PIXEL_PER_LAUNCH * local_pixels)
-    launches_per_step = max(kernel_launches, 1) / args.steps      # > 1 when the spp are chunked to the scratch budget
-    achieved = alg_bytes / (k_ms * launches_per_step * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_pathtrace_pool" if kernel == N.KERNEL_PERSISTENT else "k_pathtrace_simple",
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": NCU_TRAFFIC_BYTES_C1 if (kernel == N.KERNEL_PERSISTENT and world == 1 and not strong) else None,
-            "algorithmic_bytes_per_launch": alg_bytes,
-            "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "kernel_ms_per_launch_by_rank": per_rank_kernel_ms, "kernel_share_of_step": kernel_ms_max / ms,
-            "note": "this path is instruction-issue bound, not HBM bound (16 B written per sample); see fp32"}
+    jit = ctx.jit_status()[1]
+    pt.refresh()
 
-    # counted work (untimed extra pass with the counting variant of the kernel)
-    fp32 = None
-    if rank == 0 and (args.counters or world == 1) and not strong:
-        ccfg, _, _, _ = scenes.cornell_box_shortest(W, H, max_bounces=BOUNCES, seed=0, kernel=kernel, count_work=True)
-        with PathTracer(ccfg, objs, cam, tm, device=local_rank) as cpt:
-            cpt.refresh()
-            cpt.pathtrace(4)
-            cpt.sync()
-            c = cpt.ctx.counters()
-        per_sample = {k: c[k] / max(c["samples"], 1) for k in ("scene_evals", "rays", "normals")}
-        flop_per_sample = (per_sample["scene_evals"] * FLOP_PER_SCENE_EVAL + per_sample["normals"] * FLOP_PER_NORMAL
-                           + per_sample["rays"] * FLOP_PER_RAY_SHADE)
-        samples_per_s_gpu = W * H * SPP / (k_ms * 1e-3)
-        tflops = flop_per_sample * samples_per_s_gpu / 1e12
-        clk = (clocks.get("sm_mhz") or sm_max_mhz) if sampler else sm_max_mhz
-        peak_tflops = info["sm_count"] * 128 * 2 * sm_max_mhz * 1e6 / 1e12
-        fp32 = {"achieved_tflops": tflops, "peak_tflops": peak_tflops, "frac": tflops / peak_tflops,
-                "flop_per_sample": flop_per_sample, "per_sample": per_sample,
-                "lane_utilisation_in_march_loop": (c["march_active"] / c["march_iters"]) if c["march_iters"] else None,
-                "sm_count": info["sm_count"], "sm_mhz_under_load": clk,
-                "peak_basis": "SMs x 128 lanes x 2 flop x clocks.max.sm"}
+    # ---- rooflines of the dominant kernel ---------------------------------------------
+    k_launches = max(t["kernel_launches"], 1)
+    k_ms = t["kernel_ms_per_step_max"] * args.steps / k_launches           # average launch duration (slowest rank)
+    launches_per_step = k_launches / args.steps                            # > 1 when the spp are chunked to the scratch budget
+    local_pixels = W * H / world
+    kname = "k_pathtrace_pool_jit" if (kernel == N.KERNEL_PERSISTENT and "active" in jit) else \
+            ("k_pathtrace_pool" if kernel == N.KERNEL_PERSISTENT else "k_pathtrace_simple")
+    roof = None
+    if rank == 0:
+        per, flop, lane, eval_flops = counted_work("cornell_box_shortest", W, H, BOUNCES, 4, R.local)
+        achieved, peak_tf = fp32_roof(flop, W * H * SPP / launches_per_step, k_ms, info["sm_count"], sm_max_mhz)
+        prof, prof_file = ncu_summary("c1")
+        traffic = None
+        if prof_file and world == 1:
+            traffic = (prof.get("dram__bytes_read.sum", 0.0) + prof.get("dram__bytes_write.sum", 0.0)) * 1e6
+        roof = {"bound": "fp32-issue", "kernel": kname, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": traffic,
+                "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch at this configuration, read from {prof_file}"
+                                 if traffic else "no tracked ncu capture of this configuration (N > 1 or file absent)"),
+                "flop_per_sample": flop, "flop_per_scene_eval": eval_flops, "per_sample": per,
+                "work_note": "ALGORITHMIC work: the reference algorithm's evaluation counts (counting twin of the kernel, 4 spp pass) x "
+                             "SURVEY 8(d)'s flops; the product kernel reaches the same bits with fewer executed flops (walls as planes, "
+                             "provable misses cut short)",
+                "lane_utilisation_in_march_loop_of_counting_twin": lane,
+                "peak_basis": f"{info['sm_count']} SMs x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz (clocks.max.sm; MEASURED_PEAKS.json has no FP32 entry)",
+                "kernel_ms_per_launch": k_ms, "kernel_ms_per_launch_by_rank": t["kernel_ms_per_launch_by_rank"],
+                "kernel_launches_per_step": launches_per_step, "kernel_share_of_step": t["kernel_ms_per_step_max"] / ms_per_step,
+                "issue_active_pct": prof.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "threads_per_instruction": prof.get("smsp__thread_inst_executed_per_inst_executed.ratio"), "ncu_source": prof_file}
+    alg_bytes = ALG_BYTES_PER_PIXEL_PER_LAUNCH * local_pixels
+    design_bytes = (DESIGN_BYTES_PER_SAMPLE * local_pixels * spp / launches_per_step if kernel == N.KERNEL_PERSISTENT
+                    else 32 * local_pixels)
+    hbm = {"bound": "hbm", "kernel": kname, "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+           "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+           "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_basis": "SURVEY 8(d): 16 B per pixel per launch (spp loop inside the kernel)",
+           "design_bytes_per_launch": design_bytes,
+           "design_basis": "16 B per SAMPLE: each path writes float4(radiance, 1) to the ordered-accumulation scratch, k_fold_samples adds them "
+                           "in sample order (bit-exact accumulation with path-granular load balance)",
+           "design_achieved_GBps": design_bytes / (k_ms * 1e-3) / 1e9,
+           "traffic": roof["traffic"] if roof else None,
+           "traffic_over_algorithmic": (roof["traffic"] / alg_bytes) if (roof and roof["traffic"]) else None,
+           "traffic_over_design": (roof["traffic"] / design_bytes) if (roof and roof["traffic"]) else None,
+           "note": "not HBM-bound by three orders of magnitude; reported because north_star asks for it"}
+    pt.close()
+
+    # ---- strong scaling at the C1 size, C4, the other configurations ------------------
+    strong = c4 = None
+    workloads = {}
+    if not args.no_blocks and kernel == N.KERNEL_PERSISTENT:
+        if world == 1:
+            if rank == 0:                  # at N = 1 the strong job IS the headline step
+                strong = {"workload": WORKLOAD, "n_gpus": 1, "scaling": "strong", "width": W, "height": H, "spp": SPP, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms_per_step, "value": value, "unit": UNIT,
+                          "kernel_ms_per_step_by_rank": [t["kernel_ms_per_step_max"]], "kernel_launches_per_step": launches_per_step,
+                          "reduce_tiles_ms": None, "image_crc32": weak_crc, "crc_note": f"crc of the {SPP} spp accumulation buffer (e2e leg download)",
+                          "alpha_checksum": checksum, "sharding": "none"}
+        else:
+            strong = strong_job(R, W, H, SPP, args.warmup, args.steps, kernel, WORKLOAD)
+        c4 = strong_job(R, 4096, 4096, 1024, 1 if world >= 4 else 0, 1, kernel,
+                        "C4: cornell_box_shortest scene, 4096x4096, 1024 spp, max 8 bounces, tile-sharded")
+        if world == 1 and rank == 0:
+            for name in ("c2", "c3"):
+                workloads[name] = run_extra(name, 2 if name == "c2" else 3, 1, R.local, sm_max_mhz)
 
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and not strong:
+    if rank == 0 and world == 1 and not args.no_cpu:
         v_aw, n_aw, dt_aw = run_cpu_oracle(CPU_SPP, hoisted=False)
         v_h, n_h, dt_h = run_cpu_oracle(CPU_SPP, hoisted=True)
         cpu = {"value": v_aw, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
@@ -447,28 +678,30 @@ def main() -> int:
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "spp_per_step": spp, "max_bounces": BOUNCES,
-                       "sharding": (f"{world} ranks, {BAND}-column interleaved bands" + ("" if strong else f", spp x {world}")) if world > 1 else "none",
+                       "sharding": f"{world} ranks, {BAND}-column interleaved bands, spp x {world}" if world > 1 else "none",
                        "l2": "flushed between steps by a 256 MiB memset on the launch stream (inside the timed region)",
-                       "kernel": args.kernel, "blocks_per_sm": info["blocks_per_sm"], "jit": ctx.jit_status()[1]},
+                       "kernel": args.kernel, "blocks_per_sm": info["blocks_per_sm"], "jit": jit},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "alpha_checksum": checksum},
-            "gpu_launches": launches,
-            "clocks": clocks if sampler else None,
+                    "alpha_checksum": checksum, "image_crc32": weak_crc},
+            "gpu_launches": t["launches"],
+            "clocks": clocks,
             "roofline": roof,
+            "roofline_hbm": hbm,
         }
-        if fp32:
-            line["fp32"] = fp32
+        if strong:
+            line["strong"] = strong
+        if c4:
+            line["c4"] = c4
+        if workloads:
+            line["workloads"] = workloads
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    pt.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    R.close()
     return 0
 
 

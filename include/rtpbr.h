@@ -139,6 +139,7 @@ enum { RTPBR_CNT_SCENE_EVALS = 0, RTPBR_CNT_RAYS = 1, RTPBR_CNT_NORMALS = 2, RTP
        RTPBR_CNT_MARCH_ACTIVE = 5,     /* lanes actually marching in those iterations         */
        RTPBR_CNT_RESOLVE_ROUNDS = 6, RTPBR_CNT_LAUNCHES = 7,
        RTPBR_CNT_RESOLVED_SLOTS = 8,   /* slots handled by resolve rounds (x / rounds / 32 = resolve occupancy) */
+       RTPBR_CNT_MLP_EVALS = 9,        /* evaluations of the neural bunny's MLP (points inside its unit sphere) */
        RTPBR_CNT_COUNT = 10 };
 
 /* replaces `ti.init(arch=ti.gpu, ...)` (src/config.py:5) + field allocation (src/fileds.py:7-13) */

@@ -25,7 +25,7 @@ SKY_BLACK, SKY_ENVMAP, SKY_GRADIENT = 0, 1, 2
 KERNEL_PERSISTENT, KERNEL_SIMPLE = 0, 1
 BUF_IMAGE_BUFFER, BUF_IMAGE_PIXELS, BUF_RAY_BUFFER, BUF_DIFF_BUFFER, BUF_DIFF_PIXELS = 0, 1, 2, 3, 4
 CNT_NAMES = ("scene_evals", "rays", "normals", "samples", "march_iters", "march_active", "resolve_rounds", "launches",
-             "resolved_slots", "reserved")
+             "resolved_slots", "mlp_evals")
 
 EXPORTS = (
     "rtpbr_create", "rtpbr_destroy", "rtpbr_set_scene", "rtpbr_set_camera", "rtpbr_set_envmap", "rtpbr_set_frame",

@@ -198,6 +198,7 @@ int rtpbr_create(const RtpbrConfig* cfg, int device, RtpbrContext** out)
     rt::fill_frame(c->P, 0);
     if (const char* j = getenv("RTPBR_JIT")) c->jit_enabled = atoi(j) != 0;
     c->P.resolve_min = 8;
+    c->P.count_mlp = cfg->count_work != 0;
     if (const char* q = getenv("RTPBR_RESOLVE_MIN")) {
         int v = atoi(q);
         if (v >= 1 && v <= 32) c->P.resolve_min = v;

@@ -67,6 +67,7 @@ struct KParams {
     int32_t tiles_per_col;   // ceil(H / 8)
     int32_t nobj;
     int32_t resolve_min;     // pool kernel: resolve when this many slots are pending (or lanes would idle)
+    int32_t count_mlp;       // count_work builds: count evaluations of the neural bunny's MLP (RTPBR_CNT_MLP_EVALS)
     DevCamera cam;
     DevGeom geom[kMaxObjects];
     DevMaterial mat[kMaxObjects];
