@@ -422,10 +422,10 @@ def synthetic_env_u8(w=3200, h=1600, seed=11):
 def environment(asset: str, exposure: float, gamma: float):
     """(processed table, description): the real .hdr when $RTPBR_ASSETS holds it, else the procedural stand-in."""
     from raytracingpbr_b200 import ibl
-    d = os.environ.get("RTPBR_ASSETS")
-    if d and os.path.exists(os.path.join(d, asset)):
-        return ibl.process(ibl.imread(os.path.join(d, asset)), exposure, gamma), f"real asset {asset} ($RTPBR_ASSETS)"
-    return ibl.process(synthetic_env_u8(), exposure, gamma), "synthetic (procedural 3200x1600 environment; set $RTPBR_ASSETS for the .hdr)"
+    for d in (os.environ.get("RTPBR_ASSETS"), os.path.join(ROOT, "tests", "assets_local")):
+        if d and os.path.exists(os.path.join(d, asset)):
+            return ibl.process(ibl.imread(os.path.join(d, asset)), exposure, gamma), f"the reference's own map assets/{asset} (staged copy)"
+    return ibl.process(synthetic_env_u8(), exposure, gamma), "synthetic (procedural 3200x1600 environment; the .hdr is not staged)"
 
 
 def run_extra(name: str, steps: int, warmup: int, device: int = 0, sm_max_mhz: float = 1965.0, with_clocks: bool = False) -> dict:

@@ -371,6 +371,46 @@ int rtpbr_refresh(RtpbrContext* c)
     return RTPBR_OK;
 }
 
+// Pool geometry and scheduling policy of an NVRTC build.  Environment knobs win; otherwise kernels with a fast region
+// (family A: short march step, small resolve phase) run 3 CTAs/SM x 80 slots per warp, regenerate paths in batches of
+// their own and leave the march loop only when 6 lanes have finished (profiles/r02_sweeps.md); everything else keeps
+// the ahead-of-time geometry.
+struct JitBuild {
+    int block, slots, min_blocks;
+    std::vector<std::string> defs;
+};
+static JitBuild jit_build_options(const rt::jit::Source& src)
+{
+    auto env_int = [](const char* name, int lo, int hi, int dflt) {
+        const char* v = getenv(name);
+        if (!v || !*v) return dflt;
+        const int x = atoi(v);
+        return x >= lo && x <= hi ? x : dflt;
+    };
+    JitBuild b;
+    b.slots = env_int("RTPBR_POOL_SLOTS", 32, 128, src.fast ? 80 : rt::kPoolSlots);
+    if (b.slots % 4 != 0) b.slots = rt::kPoolSlots;
+    b.block = env_int("RTPBR_POOL_BLOCK", 32, 1024, rt::kPoolBlock);
+    if (b.block % 32 != 0) b.block = rt::kPoolBlock;
+    b.min_blocks = env_int("RTPBR_POOL_MIN_BLOCKS", 1, 16, src.fast ? 3 : rt::kPoolMinBlocks);
+    const int regen_min = env_int("RTPBR_REGEN_MIN", 0, 32, src.fast ? 24 : 0);
+    const int regen_idle = env_int("RTPBR_REGEN_IDLE", 1, 32, src.fast ? 8 : 1);
+    const int fin_min = env_int("RTPBR_FIN_MIN", 1, 32, src.fast ? 6 : 1);
+    b.defs = { "-DRT_POOL_BLOCK=" + std::to_string(b.block), "-DRT_POOL_SLOTS=" + std::to_string(b.slots),
+               "-DRT_POOL_MIN_BLOCKS=" + std::to_string(b.min_blocks) };
+    if (regen_min > 0) b.defs.push_back("-DRT_REGEN_MIN=" + std::to_string(regen_min));
+    if (regen_idle > 1) b.defs.push_back("-DRT_REGEN_IDLE=" + std::to_string(regen_idle));
+    if (fin_min > 1) b.defs.push_back("-DRT_FIN_MIN=" + std::to_string(fin_min));
+    if (const char* v = getenv("RTPBR_MARCH_UNROLL")) {
+        if (atoi(v) == 2) b.defs.push_back("-DRT_MARCH_VOTE_EVERY_2=1");
+    }
+    if (const char* v = getenv("RTPBR_POOL_MIN_BLOCKS_BUNNY")) {
+        const int x = atoi(v);
+        if (x >= 1 && x <= 16) b.defs.push_back("-DRT_POOL_MIN_BLOCKS_BUNNY=" + std::to_string(x));
+    }
+    return b;
+}
+
 // Launch sequence of one rtpbr_pathtrace call.
 //   families A/B, pool kernel: the spp are processed in chunks sized so that the per-sample scratch
 //   buffer ([pixel items][chunk] float4) stays within the scratch budget (RTPBR_SCRATCH_MB, default
@@ -403,37 +443,12 @@ static void ensure_jit(RtpbrContext* c)
     const rt::jit::Source src = rt::jit::generate(c->cfg, c->scene.data(), (int)c->scene.size(), max_pairs);
     std::shared_ptr<std::vector<char>> cubin;
     std::string log;
-    // Pool geometry and scheduling policy of the NVRTC build.  Environment knobs win; otherwise kernels with a fast region
-    // (family A: short march step, small resolve phase) run 3 CTAs/SM x 80 slots per warp, regenerate paths in batches of
-    // their own and leave the march loop only when 6 lanes have finished (profiles/r02_sweeps.md); everything else keeps
-    // the ahead-of-time geometry.
-    auto env_int = [](const char* name, int lo, int hi, int dflt) {
-        const char* v = getenv(name);
-        if (!v || !*v) return dflt;
-        const int x = atoi(v);
-        return x >= lo && x <= hi ? x : dflt;
-    };
-    c->jit_slots = env_int("RTPBR_POOL_SLOTS", 32, 128, src.fast ? 80 : rt::kPoolSlots);
-    if (c->jit_slots % 4 != 0) c->jit_slots = rt::kPoolSlots;
-    c->jit_block = env_int("RTPBR_POOL_BLOCK", 32, 1024, rt::kPoolBlock);
-    if (c->jit_block % 32 != 0) c->jit_block = rt::kPoolBlock;
-    c->jit_min_blocks = env_int("RTPBR_POOL_MIN_BLOCKS", 1, 16, src.fast ? 3 : rt::kPoolMinBlocks);
-    const int regen_min = env_int("RTPBR_REGEN_MIN", 0, 32, src.fast ? 24 : 0);
-    const int regen_idle = env_int("RTPBR_REGEN_IDLE", 1, 32, src.fast ? 8 : 1);
-    const int fin_min = env_int("RTPBR_FIN_MIN", 1, 32, src.fast ? 6 : 1);
+    const JitBuild build = jit_build_options(src);
+    c->jit_slots = build.slots;
+    c->jit_block = build.block;
+    c->jit_min_blocks = build.min_blocks;
     const size_t smem = rt::pool_smem_bytes_for(c->jit_block, c->jit_slots);
-    std::vector<std::string> defs = { "-DRT_POOL_BLOCK=" + std::to_string(c->jit_block), "-DRT_POOL_SLOTS=" + std::to_string(c->jit_slots),
-                                      "-DRT_POOL_MIN_BLOCKS=" + std::to_string(c->jit_min_blocks) };
-    if (regen_min > 0) defs.push_back("-DRT_REGEN_MIN=" + std::to_string(regen_min));
-    if (regen_idle > 1) defs.push_back("-DRT_REGEN_IDLE=" + std::to_string(regen_idle));
-    if (fin_min > 1) defs.push_back("-DRT_FIN_MIN=" + std::to_string(fin_min));
-    if (const char* v = getenv("RTPBR_MARCH_UNROLL")) {
-        if (atoi(v) == 2) defs.push_back("-DRT_MARCH_VOTE_EVERY_2=1");
-    }
-    if (const char* v = getenv("RTPBR_POOL_MIN_BLOCKS_BUNNY")) {
-        const int x = atoi(v);
-        if (x >= 1 && x <= 16) defs.push_back("-DRT_POOL_MIN_BLOCKS_BUNNY=" + std::to_string(x));
-    }
+    const std::vector<std::string>& defs = build.defs;
     std::string key = src.text;
     for (const std::string& d : defs) key += "\n" + d;
     if (c->jit_kernel && key == c->jit_key) return;          // same translation unit as the loaded kernel
@@ -790,7 +805,7 @@ int rtpbr_jit_compile_check(const RtpbrConfig* cfg, const RtpbrObject* objects, 
     const rt::jit::Source src = rt::jit::generate(*cfg, objects, n);
     std::shared_ptr<std::vector<char>> cubin;
     std::string l;
-    const bool ok = rt::jit::compile(src.text, rt::jit::default_include_dir(), cubin, l);
+    const bool ok = rt::jit::compile(src.text, rt::jit::default_include_dir(), cubin, l, jit_build_options(src).defs);   // the options rtpbr_pathtrace uses
     if (log && cap > 0) {
         strncpy(log, l.c_str(), cap - 1);
         log[cap - 1] = '\0';
