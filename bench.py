@@ -85,9 +85,13 @@ def ncu_summary(tag: str):
             for row in csv.reader(f):
                 if len(row) >= 3:
                     try:
-                        out[row[0]] = float(row[2])
+                        v = float(row[2])
                     except ValueError:
-                        pass
+                        continue
+                    unit = row[1].strip().lower()
+                    if row[0].startswith("dram__bytes"):          # ncu picks the unit per capture: normalise to MB
+                        v *= {"byte": 1e-6, "kbyte": 1e-3, "mbyte": 1.0, "gbyte": 1e3}.get(unit, 1.0)
+                    out[row[0]] = v
         if out:
             return out, os.path.relpath(path, ROOT)
     return {}, None

@@ -131,7 +131,8 @@ enum { RTPBR_BUF_IMAGE_BUFFER = 0,  /* image_buffer  vec4 f32 (W,H,4), src/filed
        RTPBR_BUF_IMAGE_PIXELS = 1,  /* image_pixels  vec3 f32 (W,H,3), src/fileds.py:9 */
        RTPBR_BUF_RAY_BUFFER = 2,    /* ray_buffer    AOS Ray, 10 x 4 bytes (W,H,10), src/fileds.py:7 */
        RTPBR_BUF_DIFF_BUFFER = 3,   /* diff_buffer   vec2 f32 (W,H,2), src/fileds.py:21 (adaptive sampling only) */
-       RTPBR_BUF_DIFF_PIXELS = 4 }; /* diff_pixels   f32 (W,H,1), src/fileds.py:22 (adaptive sampling only) */
+       RTPBR_BUF_DIFF_PIXELS = 4,   /* diff_pixels   f32 (W,H,1), src/fileds.py:22 (adaptive sampling only) */
+       RTPBR_BUF_DENOISE_PIXELS = 5 }; /* denoise_pixels vec3 f32 (W,H,3), examples/denoise/denoise_test_1.py:53 (after rtpbr_denoise) */
 
 /* counters written by rtpbr_get_counters (valid when count_work = 1) */
 enum { RTPBR_CNT_SCENE_EVALS = 0, RTPBR_CNT_RAYS = 1, RTPBR_CNT_NORMALS = 2, RTPBR_CNT_SAMPLES = 3,
@@ -171,6 +172,13 @@ RTPBR_API int rtpbr_pathtrace(RtpbrContext* ctx, int spp);
  * (cornell_box_shortest.py:124-129).  mode: 0 family A, 1 family B, 2 family C, 3 v3. */
 RTPBR_API int rtpbr_post_process(RtpbrContext* ctx, int mode, float exposure, double gamma);  /* gamma in binary64: the
    reference folds 1.0 / camera_gamma in Python before casting to f32 (src/postprocessor.py:32) */
+
+/* replaces kernel denoise(image_pixels, denoise_pixels, threshold) of examples/denoise/denoise_test_1.py:86-118 (the
+ * temporal blend + bright-neighbour fill after shadertoy 7tKGzD) as an optional pass after rtpbr_post_process.  The
+ * reference filters denoise_pixels in place while neighbouring threads read it, so its own result depends on the thread
+ * schedule; this entry point is the deterministic form: neighbours are read from the previous denoise_pixels, the result
+ * becomes the new denoise_pixels (double-buffered; zero before the first call, like a fresh Taichi field). */
+RTPBR_API int rtpbr_denoise(RtpbrContext* ctx, float threshold);
 
 /* replaces field.to_numpy() / canvas.set_image(field) / ti.tools.imwrite(field) reads */
 RTPBR_API int rtpbr_download(RtpbrContext* ctx, int which, void* host, size_t bytes);

@@ -270,6 +270,19 @@ def pathtrace_adaptive(cfg: OrcConfig, objs, launches: int, image_buffer, ray_bu
         raise RuntimeError(f"orc_pathtrace_adaptive failed: {rc}")
 
 
+def denoise(pixels_in: np.ndarray, out_prev: np.ndarray, threshold: float) -> np.ndarray:
+    """One deterministic pass of kernel denoise() (examples/denoise/denoise_test_1.py:86-118); returns the new output."""
+    W, H, _ = pixels_in.shape
+    pixels_in = np.ascontiguousarray(pixels_in, dtype=np.float32)
+    out_prev = np.ascontiguousarray(out_prev, dtype=np.float32)
+    out = np.empty_like(pixels_in)
+    L = lib()
+    L.orc_denoise.restype = None
+    L.orc_denoise.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float]
+    L.orc_denoise(W, H, _f32p(pixels_in), _f32p(out_prev), _f32p(out), threshold)
+    return out
+
+
 def post_process_src(image_buffer, image_pixels, diff_buffer, diff_pixels, exposure: float, gamma: float, adaptive: bool):
     """kernel post_process() of src/postprocessor.py:24-43, in place on image_pixels / diff_*."""
     n = image_buffer.shape[0] * image_buffer.shape[1]

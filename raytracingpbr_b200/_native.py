@@ -23,7 +23,7 @@ FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2
 MARCH_PLAIN, MARCH_ENHANCED, MARCH_SRC = 0, 1, 2
 SKY_BLACK, SKY_ENVMAP, SKY_GRADIENT = 0, 1, 2
 KERNEL_PERSISTENT, KERNEL_SIMPLE = 0, 1
-BUF_IMAGE_BUFFER, BUF_IMAGE_PIXELS, BUF_RAY_BUFFER, BUF_DIFF_BUFFER, BUF_DIFF_PIXELS = 0, 1, 2, 3, 4
+BUF_IMAGE_BUFFER, BUF_IMAGE_PIXELS, BUF_RAY_BUFFER, BUF_DIFF_BUFFER, BUF_DIFF_PIXELS, BUF_DENOISE_PIXELS = 0, 1, 2, 3, 4, 5
 CNT_NAMES = ("scene_evals", "rays", "normals", "samples", "march_iters", "march_active", "resolve_rounds", "launches",
              "resolved_slots", "mlp_evals")
 
@@ -37,7 +37,7 @@ EXPORTS = (
     "rtpbr_multi_create", "rtpbr_multi_destroy", "rtpbr_multi_count", "rtpbr_multi_context", "rtpbr_multi_set_scene",
     "rtpbr_multi_set_camera", "rtpbr_multi_set_envmap", "rtpbr_multi_set_frame", "rtpbr_multi_set_sample_base",
     "rtpbr_multi_refresh", "rtpbr_multi_pathtrace", "rtpbr_multi_reduce", "rtpbr_multi_post_process",
-    "rtpbr_multi_download", "rtpbr_multi_sync", "rtpbr_device_count",
+    "rtpbr_multi_download", "rtpbr_multi_sync", "rtpbr_device_count", "rtpbr_denoise",
 )
 
 
@@ -139,6 +139,7 @@ def lib() -> C.CDLL:
         "rtpbr_jit_compile_check": [C.POINTER(RtpbrConfig), C.POINTER(RtpbrObject), C.c_int, C.c_char_p, C.c_size_t],
         "rtpbr_version": [], "rtpbr_sizeof_config": [], "rtpbr_sizeof_object": [], "rtpbr_sizeof_camera": [],
         "rtpbr_device_count": [],
+        "rtpbr_denoise": [vp, C.c_float],
         "rtpbr_multi_create": [C.POINTER(RtpbrConfig), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)],
         "rtpbr_multi_destroy": [vp],
         "rtpbr_multi_count": [vp],
@@ -319,6 +320,9 @@ class Context:
     def post_process(self, mode: int, exposure: float = 1.0, gamma: float = 2.2) -> None:
         check(self._L.rtpbr_post_process(self._h, mode, exposure, gamma))
 
+    def denoise(self, threshold: float) -> None:
+        check(self._L.rtpbr_denoise(self._h, float(threshold)))
+
     def sync(self) -> None:
         check(self._L.rtpbr_sync(self._h))
 
@@ -338,7 +342,7 @@ class Context:
 
     # -- data -------------------------------------------------------------------------
     def download(self, which: int = BUF_IMAGE_BUFFER, out: np.ndarray | None = None) -> np.ndarray:
-        ch = {BUF_IMAGE_BUFFER: 4, BUF_IMAGE_PIXELS: 3, BUF_RAY_BUFFER: 10, BUF_DIFF_BUFFER: 2, BUF_DIFF_PIXELS: 1}[which]
+        ch = {BUF_IMAGE_BUFFER: 4, BUF_IMAGE_PIXELS: 3, BUF_RAY_BUFFER: 10, BUF_DIFF_BUFFER: 2, BUF_DIFF_PIXELS: 1, BUF_DENOISE_PIXELS: 3}[which]
         if out is None:
             out = np.empty((self.width, self.height, ch), dtype=np.float32)
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.width, self.height, ch)
@@ -473,7 +477,7 @@ class MultiContext:
         check(self._L.rtpbr_multi_sync(self._h))
 
     def download(self, which: int = BUF_IMAGE_BUFFER, out: np.ndarray | None = None) -> np.ndarray:
-        ch = {BUF_IMAGE_BUFFER: 4, BUF_IMAGE_PIXELS: 3, BUF_RAY_BUFFER: 10, BUF_DIFF_BUFFER: 2, BUF_DIFF_PIXELS: 1}[which]
+        ch = {BUF_IMAGE_BUFFER: 4, BUF_IMAGE_PIXELS: 3, BUF_RAY_BUFFER: 10, BUF_DIFF_BUFFER: 2, BUF_DIFF_PIXELS: 1, BUF_DENOISE_PIXELS: 3}[which]
         if out is None:
             out = np.empty((self.width, self.height, ch), dtype=np.float32)
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.width, self.height, ch)

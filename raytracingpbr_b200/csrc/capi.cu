@@ -92,6 +92,8 @@ struct RtpbrContext {
     float* d_ray_buffer = nullptr;
     float* d_diff_buffer = nullptr;   // adaptive sampling (family C): vec2 per pixel
     float* d_diff_pixels = nullptr;   // adaptive sampling: f32 per pixel
+    float* d_denoise[2] = { nullptr, nullptr };   // denoise_pixels, double-buffered (allocated by the first rtpbr_denoise)
+    int denoise_cur = 0;
     float* d_rr = nullptr;
     float* d_env = nullptr;
     unsigned long long* d_work = nullptr;
@@ -264,6 +266,8 @@ int rtpbr_destroy(RtpbrContext* c)
     cudaFree(c->d_ray_buffer);
     cudaFree(c->d_diff_buffer);
     cudaFree(c->d_diff_pixels);
+    cudaFree(c->d_denoise[0]);
+    cudaFree(c->d_denoise[1]);
     cudaFree(c->d_rr);
     cudaFree(c->d_env);
     cudaFree(c->d_work);
@@ -610,6 +614,27 @@ int rtpbr_post_process(RtpbrContext* c, int mode, float exposure, double gamma)
     return RTPBR_OK;
 }
 
+int rtpbr_denoise(RtpbrContext* c, float threshold)
+{
+    if (!c) return fail(RTPBR_ERR_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t bytes = npixels(c) * 3 * sizeof(float);
+    if (!c->d_denoise[0]) {
+        CUDA_TRY(cudaMalloc(&c->d_denoise[0], bytes));
+        if (cudaMalloc(&c->d_denoise[1], bytes) != cudaSuccess) {
+            cudaFree(c->d_denoise[0]);
+            c->d_denoise[0] = nullptr;
+            return fail(RTPBR_ERR_CUDA, "cudaMalloc(denoise_pixels) failed");
+        }
+        CUDA_TRY(cudaMemsetAsync(c->d_denoise[0], 0, bytes, c->stream));
+        c->denoise_cur = 0;
+    }
+    const int prev = c->denoise_cur, next = 1 - prev;
+    CUDA_TRY(rt::launch_denoise(c->d_image_pixels, c->d_denoise[prev], c->d_denoise[next], c->cfg.width, c->cfg.height, threshold, c->stream));
+    c->denoise_cur = next;
+    return RTPBR_OK;
+}
+
 static int buffer_of(RtpbrContext* c, int which, void** ptr, size_t* bytes)
 {
     switch (which) {
@@ -624,6 +649,9 @@ static int buffer_of(RtpbrContext* c, int which, void** ptr, size_t* bytes)
     case RTPBR_BUF_DIFF_PIXELS:
         if (!c->d_diff_pixels) return fail(RTPBR_ERR_STATE, "diff_pixels exists with adaptive_sampling only");
         *ptr = c->d_diff_pixels; *bytes = npixels(c) * sizeof(float); return RTPBR_OK;
+    case RTPBR_BUF_DENOISE_PIXELS:
+        if (!c->d_denoise[0]) return fail(RTPBR_ERR_STATE, "denoise_pixels exists after the first rtpbr_denoise");
+        *ptr = c->d_denoise[c->denoise_cur]; *bytes = npixels(c) * 3 * sizeof(float); return RTPBR_OK;
     default: return fail(RTPBR_ERR_ARG, "unknown buffer");
     }
 }

@@ -172,6 +172,33 @@ __global__ void __launch_bounds__(256) k_post_process_src(const float4* __restri
     }
 }
 
+// kernel denoise() of examples/denoise/denoise_test_1.py:86-118 as one DETERMINISTIC pass: the reference filters
+// pixels_out in place while neighbouring threads read it (a race); here every neighbour comes from the previous output
+// and the result goes to a second buffer (capi.cu swaps them).  28 B read + 12 B written per pixel (+ 4 neighbours from L2).
+__global__ void __launch_bounds__(256) k_denoise(const float* __restrict__ pixels_in, const float* __restrict__ out_prev,
+                                                 float* __restrict__ out_new, int W, int H, float threshold)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int i = p / H, j = p - i * H;
+    const vec3 pixel1 = V3(pixels_in[3 * p], pixels_in[3 * p + 1], pixels_in[3 * p + 2]);
+    const vec3 pixel2 = V3(out_prev[3 * p], out_prev[3 * p + 1], out_prev[3 * p + 2]);
+    vec3 col = mix3(pixel1, pixel2, 0.2f);
+    if (brightness(pixel1) < threshold) {
+        const int ip = min(i + 1, W - 1), im = max(i - 1, 0), jp = min(j + 1, H - 1);
+        const int q[4] = { ip * H + j, im * H + j, i * H + jp, i * H + jp };      // sur3 repeats j + 1, as written (:95-96)
+        vec3 sum = V3(0.0f);
+        float counter = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const vec3 sur = V3(out_prev[3 * q[k]], out_prev[3 * q[k] + 1], out_prev[3 * q[k] + 2]);
+            if (brightness(sur) > threshold) { sum = sum + sur; counter += 1.0f; }
+        }
+        col = V3(sum.x / counter, sum.y / counter, sum.z / counter);           // 0 / 0 = NaN when no neighbour qualifies (:113)
+    }
+    out_new[3 * p] = col.x; out_new[3 * p + 1] = col.y; out_new[3 * p + 2] = col.z;
+}
+
 // refresh() with ADAPTIVE_SAMPLING: diff_buffer = vec2(1), diff_pixels = 1e32 (src/renderer.py:18-20)
 __global__ void __launch_bounds__(256) k_refresh_adaptive(float2* diff_buffer, float* diff_pixels, int n)
 {
@@ -285,6 +312,11 @@ cudaError_t launch_post_process_src(const float4* image_buffer, float* image_pix
 cudaError_t launch_refresh_adaptive(float* diff_buffer, float* diff_pixels, int n, cudaStream_t stream)
 {
     k_refresh_adaptive<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<float2*>(diff_buffer), diff_pixels, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_denoise(const float* pixels_in, const float* out_prev, float* out_new, int W, int H, float threshold, cudaStream_t stream)
+{
+    k_denoise<<<(W * H + 255) / 256, 256, 0, stream>>>(pixels_in, out_prev, out_new, W, H, threshold);
     return cudaGetLastError();
 }
 cudaError_t launch_post_process(const float4* image_buffer, float* image_pixels, int n, int mode, float exposure,

@@ -26,6 +26,7 @@ cudaError_t launch_refresh_depth(float* ray_buffer, int n, cudaStream_t stream);
 cudaError_t launch_post_process_src(const float4* image_buffer, float* image_pixels, float* diff_buffer, float* diff_pixels, int n,
                                     float exposure, float gamma_inv, cudaStream_t stream);
 cudaError_t launch_refresh_adaptive(float* diff_buffer, float* diff_pixels, int n, cudaStream_t stream);
+cudaError_t launch_denoise(const float* pixels_in, const float* out_prev, float* out_new, int W, int H, float threshold, cudaStream_t stream);
 cudaError_t launch_post_process(const float4* image_buffer, float* image_pixels, int n, int mode, float exposure,
                                 float inv_gamma, cudaStream_t stream);
 

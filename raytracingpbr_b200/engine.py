@@ -35,8 +35,11 @@ class PathTracer:
         self.image_buffer = Field(self.ctx, N.BUF_IMAGE_BUFFER, 4)     # src/fileds.py:8
         self.image_pixels = Field(self.ctx, N.BUF_IMAGE_PIXELS, 3)     # src/fileds.py:9
         self.ray_buffer = Field(self.ctx, N.BUF_RAY_BUFFER, 10)        # src/fileds.py:7 (family C only)
+        self.denoise_pixels = Field(self.ctx, N.BUF_DENOISE_PIXELS, 3) # denoise_test_1.py:53 (after the first denoise())
         self.set_scene(objects)
         self.set_camera(camera)
+        if self.tonemap.get("frame"):                 # presets with an animation frame (scenes.bunny_glass(frame=...))
+            self.set_frame(int(self.tonemap["frame"]))
 
     # scene / camera ----------------------------------------------------------------------
     def set_scene(self, objects) -> None:
@@ -51,6 +54,10 @@ class PathTracer:
         """Processed environment table, (w, h, 3) f32 (see raytracingpbr_b200.ibl)."""
         self.ctx.set_envmap(table)
 
+    def set_frame(self, frame: int) -> None:
+        """`u_frame[None] = frame` (bunny_sdf_glass.py:409): the neural bunny's programmatic rotation + bob."""
+        self.ctx.set_frame(frame)
+
     # frame loop --------------------------------------------------------------------------
     def refresh(self) -> None:
         """kernel refresh(), src/renderer.py:12-22."""
@@ -63,6 +70,11 @@ class PathTracer:
     def post_process(self) -> None:
         """kernel post_process(), src/postprocessor.py:24-38 (variant chosen by the preset)."""
         self.ctx.post_process(self.tonemap["mode"], self.tonemap["exposure"], self.tonemap["gamma"])
+
+    def denoise(self, threshold: float = 0.1) -> None:
+        """kernel denoise(image_pixels, denoise_pixels, threshold), examples/denoise/denoise_test_1.py:86-118, as a
+        deterministic double-buffered pass over the tone-mapped pixels; result in `denoise_pixels`."""
+        self.ctx.denoise(threshold)
 
     def render(self, spp: int = 1, refreshing: bool = False) -> None:
         """render(refreshing), src/renderer.py:25-32."""
@@ -122,6 +134,8 @@ class MultiPathTracer:
         self.image_pixels = Field(self.ctx, N.BUF_IMAGE_PIXELS, 3)
         self.set_scene(objects)
         self.set_camera(camera)
+        if self.tonemap.get("frame"):
+            self.set_frame(int(self.tonemap["frame"]))
 
     def set_scene(self, objects) -> None:
         self.objects = list(objects)

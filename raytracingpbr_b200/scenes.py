@@ -249,7 +249,7 @@ def bunny_glass(width: int = 1920, height: int = 1080, max_bounces: int = 512, s
     c.sky = N.SKY_ENVMAP
     objects = [_obj(SHAPE_BUNNY, (0, 0, 0), (-90, 0, 0), (1, 1, 1), vec3(1, 1, 1) * 0.9, vec3(1), 0, 0, 1, 1.500)]   # :221-225
     camera = Camera(vec3(0, 0, 4), vec3(0, 0, 3), vec3(0, 1, 0), 30.0, width / height, 0.03, 4.0)     # :34-37, :435
-    tonemap = dict(mode=1, exposure=0.8, gamma=2.2)  # :423-432
+    tonemap = dict(mode=1, exposure=0.8, gamma=2.2, frame=int(frame))  # :423-432; `frame`: u_frame (:409), applied by PathTracer
     return c, objects, camera, tonemap
 
 

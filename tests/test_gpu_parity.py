@@ -295,3 +295,28 @@ def test_src_shaped_modules_drive_the_same_kernels():
         assert np.array_equal(got, pt.image_buffer.to_numpy())
         assert np.array_equal(pix, pt.image_pixels.to_numpy())
     assert got[..., 3].sum() > 0 and pix.max() <= 1.0
+
+
+def test_denoise_pass_equals_the_oracle_bit_for_bit():
+    """rtpbr_denoise: the deterministic (double-buffered) form of kernel denoise(), examples/denoise/denoise_test_1.py:86-118."""
+    rng = np.random.default_rng(8)
+    W, H = 96, 64
+    cfg, objs, cam, tm = scenes.cornell_box_shortest(W, H, max_bounces=3, seed=2)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        prev = np.zeros((W, H, 3), np.float32)                       # a fresh Taichi field
+        for it, thr in enumerate((0.1, 0.35, 0.02)):
+            pix = (rng.random((W, H, 3)) ** 3).astype(np.float32)    # mostly dark with bright outliers, like a noisy render
+            pix[rng.random((W, H)) < 0.3] = 0.0
+            pt.image_pixels.from_numpy(pix)
+            pt.denoise(thr)
+            got = pt.denoise_pixels.to_numpy()
+            want = po.denoise(pix, prev, thr)
+            assert np.array_equal(got, want, equal_nan=True), it
+            assert np.isnan(want).any() == np.isnan(got).any()
+            prev = want
+        assert np.isnan(prev).any()                                  # dark pixel without a bright neighbour: 0 / 0, as written
+    # on a real render: the filter only ever blends / fills, it never brightens beyond the brightest input
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.refresh(); pt.pathtrace(2); pt.post_process(); pt.denoise(1e-3)
+        a, b = pt.image_pixels.to_numpy(), pt.denoise_pixels.to_numpy()
+        assert np.nanmax(b) <= a.max() + 1e-6

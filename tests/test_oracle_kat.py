@@ -231,3 +231,39 @@ def test_two_ahead_draws_are_the_same_stream():
             po.lib().orc_philox4x32_10((C.c_uint32 * 4)(pixel, launch, (n + k) >> 2, 0), (C.c_uint32 * 2)(seed, 0x52545042), raw)
             want.append(np.float32(raw[(n + k) & 3] >> 8) * np.float32(2.0 ** -24))
         assert np.array_equal(np.asarray(want, np.float32).view(np.uint32), v[0:3].view(np.uint32))
+
+
+def test_denoise_restatement_against_a_python_transcription():
+    """orc_denoise vs a line-by-line Python transcription of kernel denoise() (examples/denoise/denoise_test_1.py:86-118)
+    with the reads taken from the previous output (the deterministic form), on a small field."""
+    import numpy as np
+    from oracle import pyoracle as po
+    f32 = np.float32
+    rng = np.random.default_rng(3)
+    W, H, thr = 7, 5, f32(0.3)
+    pin = (rng.random((W, H, 3)) ** 2).astype(f32)
+    pin[rng.random((W, H)) < 0.4] *= f32(0.05)
+    prev = rng.random((W, H, 3)).astype(f32)
+
+    def fma(a, b, c):                    # one rounding, like fmaf
+        return f32(np.float64(a) * np.float64(b) + np.float64(c))
+
+    def bright(c):                       # dot contract: fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x))
+        return fma(c[2], f32(0.114), fma(c[1], f32(0.587), f32(c[0] * f32(0.299))))
+
+    want = np.empty_like(pin)
+    for i in range(W):
+        for j in range(H):
+            p1, p2 = pin[i, j], prev[i, j]
+            col = np.array([f32(f32(a * f32(f32(1.0) - f32(0.2))) + f32(b * f32(0.2))) for a, b in zip(p1, p2)], f32)   # mix
+            if bright(p1) < thr:
+                sur = [prev[min(i + 1, W - 1), j], prev[max(i - 1, 0), j], prev[i, min(j + 1, H - 1)], prev[i, min(j + 1, H - 1)]]
+                s, n = np.zeros(3, f32), f32(0)
+                for q in sur:
+                    if bright(q) > thr:
+                        s, n = (s + q).astype(f32), f32(n + 1)
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    col = (s / n).astype(f32)
+            want[i, j] = col
+    got = po.denoise(pin, prev, float(thr))
+    assert np.array_equal(got, want, equal_nan=True)
