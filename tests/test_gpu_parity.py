@@ -242,6 +242,20 @@ def test_packed_division_by_1_4_is_ieee_for_every_float(tmp_path):
     assert total == 2 ** 32 and fast == 2 * 201 * 2 ** 23     # exponent fields 27..227, both signs
 
 
+def test_packed_sine_of_the_bunny_mlp_equals_the_contract_sine_for_every_float_in_range(tmp_path):
+    """sin2_rt (magic-number rounding, sign-bit xor; rt_integrator.cuh) against sin_rt() on the device for every binary32
+    value with |x| * 2/pi < 2^22 -- far beyond the MLP's pre-activations, which stay below 64 (tests/test_oracle_kat.py)."""
+    import subprocess
+    exe = tmp_path / "sin2_check"
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-prec-div=true",
+                           "-prec-sqrt=true", "-o", str(exe), os.path.join(common.ROOT, "tests", "native", "sin2_check.cu")],
+                          stderr=subprocess.DEVNULL)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    total, bad = (int(x) for x in out.stdout.split())
+    assert out.returncode == 0 and bad == 0, out.stdout
+    assert total > 2 * 1_250_000_000
+
+
 def test_c4_resolution_4096_sharded_property():
     # configs[4]: 4096 x 4096 tile-sharded over 8 ranks; here one GPU renders shard 3 of 8 and a 1-rank crop check
     part = render(4096, 4096, 1, 8, shard=(3, 8, 4))

@@ -2,6 +2,7 @@
  and Philox4x32-10 to the Random123 vectors."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -267,3 +268,29 @@ def test_denoise_restatement_against_a_python_transcription():
             want[i, j] = col
     got = po.denoise(pin, prev, float(thr))
     assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_bunny_mlp_sine_arguments_are_bounded():
+    """Precondition of the device's packed sine (sin2_rt): every pre-activation of the neural bunny stays far below
+    2^22 * pi/2.  Bound from the weight tables (csrc/bunny_weights.h): inputs |p| <= 1 per coordinate (the MLP is only
+    evaluated inside the unit sphere), first activations in [-1, 1], second in [-2, 2] (sin + residual)."""
+    import re
+    import numpy as np
+    txt = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "raytracingpbr_b200", "csrc", "bunny_weights.h")).read()
+    txt = txt.replace("\\\n", " ")
+
+    def table(name):
+        m = re.search(r"#define BUNNY_%s_INIT (.*)" % name, txt)
+        return np.array([float(v) for v in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?(?=f)", m.group(1))])
+    wy, wz, wx, b1 = table("WY"), table("WZ"), table("WX"), table("B1")
+    m2, b2, m3, b3 = table("M2").reshape(4, 4, 16), table("B2"), table("M3").reshape(4, 4, 16), table("B3")
+    assert len(wy) == 16 and m2.size == 256 and m3.size == 256
+    x1 = np.abs(wy) + np.abs(wz) + np.abs(wx) + np.abs(b1)
+    # out[4g + j] = sum_h sum_k in[4h + k] * M[g][h][4k + j] + B[4g + j]
+    col2 = np.abs(m2).reshape(4, 4, 4, 4).sum(axis=(1, 2)).reshape(16)      # sum over (h, k) for every (g, j)
+    col3 = np.abs(m3).reshape(4, 4, 4, 4).sum(axis=(1, 2)).reshape(16)
+    x2 = 1.0 * col2 + np.abs(b2)
+    x3 = 2.0 * col3 + np.abs(b3)
+    worst = max(x1.max(), x2.max(), x3.max()) * 1.001
+    assert worst < 64.0, worst
+    assert worst * 2 / np.pi < 2 ** 22 / 1e4
