@@ -412,6 +412,9 @@ static JitBuild jit_build_options(const rt::jit::Source& src)
         const int x = atoi(v);
         if (x >= 1 && x <= 16) b.defs.push_back("-DRT_POOL_MIN_BLOCKS_BUNNY=" + std::to_string(x));
     }
+    if (const char* v = getenv("RTPBR_SIN4_INLINE")) {          // tuning knob: the MLP's sine routine inlined at its 12 call sites
+        if (atoi(v) != 0) b.defs.push_back("-DRT_SIN4_INLINE=1");
+    }
     return b;
 }
 
