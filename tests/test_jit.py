@@ -183,13 +183,17 @@ def test_specialised_source_carries_the_right_variant_switches():
 _JIT_HC = {}
 
 
-def jit_hostcheck(name, tmp_path_factory):
-    """tests/native/hostcheck.cu compiled together with the scene-specialised translation unit of preset `name`, with
-    both analyses forced on wherever they apply (the automatic policy keeps them for the scenes where they pay)."""
+def jit_hostcheck(name, tmp_path_factory, scene=None):
+    """tests/native/hostcheck.cu compiled together with the scene-specialised translation unit of preset `name` (or of the
+    explicit `scene` = (cfg, objs, cam)), with both analyses forced on wherever they apply (the automatic policy keeps
+    them for the scenes where they pay)."""
     if name in _JIT_HC:
         return _JIT_HC[name]
-    preset = PRESETS[name][0]
-    cfg, objs, cam, _ = preset(40, 32, seed=5, max_bounces=6)
+    if scene is not None:
+        cfg, objs, cam = scene
+    else:
+        preset = PRESETS[name][0]
+        cfg, objs, cam, _ = preset(40, 32, seed=5, max_bounces=6)
     old = {k: os.environ.get(k) for k in ("RTPBR_JIT_FAST", "RTPBR_JIT_BBOX")}
     os.environ.update(RTPBR_JIT_FAST="1", RTPBR_JIT_BBOX="1")
     try:
@@ -289,6 +293,72 @@ def test_specialised_march_renders_the_same_image_on_host(name, tmp_path_factory
                                   3, 3, 0, 0, 1, 32, None)
     assert rc == 0
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_scene_analyses_on_random_rooms(seed, tmp_path_factory):
+    """The code generator's analyses on scenes nobody tuned: rooms made of axis-aligned slabs with random extents,
+    offsets and quarter-turn rotations (so that the near-permutation matrices carry the reference's -4.4e-8 entries in
+    every position and sign), plus freely rotated boxes inside; family A and the PBR family with rounded boxes.  The fast
+    function must have the bits of the full one wherever it says ok, and whole marches must end like the generic ones."""
+    from raytracingpbr_b200.dataclass import Material, SDFObject, Transform
+    from raytracingpbr_b200.tmath import vec3
+    rng = np.random.default_rng(seed)
+    half = float(rng.uniform(0.6, 3.0))
+    thick = float(rng.uniform(0.05, 0.3)) * half
+    centre = rng.uniform(-0.5, 0.5, 3) * float(rng.choice([0.0, 1.0]))
+    quarter = [0.0, 90.0, 180.0, 270.0, -90.0]
+    objs = []
+    for axis in range(3):
+        for sign in (-1.0, 1.0):
+            if axis == 2 and sign > 0 and seed % 2:
+                continue                                                    # open front, like the Cornell box
+            pos = centre.copy()
+            pos[axis] += sign * half
+            # the slab's thin extent must end up along `axis` after the rotation: build it in world axes, then pick a
+            # rotation made of quarter turns and permute the scale accordingly (any of them is a valid description)
+            scale = [half * 1.2, half * 1.2, half * 1.2]
+            scale[axis] = thick
+            rot = [float(rng.choice(quarter)) if rng.random() < 0.5 else 0.0 for _ in range(3)]
+            m = np.zeros(9, np.float32)
+            common.hostcheck().hostcheck_euler((C.c_float * 3)(*rot), m.ctypes.data_as(C.POINTER(C.c_float)))
+            perm = np.abs(m.reshape(3, 3)).argmax(axis=1)                   # local axis r looks along world axis perm[r]
+            local = [scale[perm[r]] for r in range(3)]
+            objs.append(SDFObject(type=scenes.SHAPE_BOX, transform=Transform(vec3(*pos), vec3(*rot), vec3(*local)),
+                                  material=Material(vec3(0.6), vec3(1), 1.0, 0.0, 0.0, 1.5)))
+    for _ in range(int(rng.integers(1, 4))):
+        objs.append(SDFObject(type=scenes.SHAPE_BOX,
+                              transform=Transform(vec3(*(centre + rng.uniform(-0.5, 0.5, 3) * half)), vec3(*rng.uniform(-180, 180, 3)),
+                                                  vec3(*rng.uniform(0.1, 0.35, 3) * half)),
+                              material=Material(vec3(0.5), vec3(1), 1.0, 0.0, 0.0, 1.5)))
+    objs.append(SDFObject(type=scenes.SHAPE_BOX, transform=Transform(vec3(*(centre + np.array([0, 0.8 * half, 0]))), vec3(0, 0, 0),
+                                                                     vec3(0.2 * half, 0.01 * half, 0.2 * half)),
+                          material=Material(vec3(1), vec3(50), 1.0, 0.0, 0.0, 1.0)))
+    for family in ("A", "B"):
+        if family == "A":
+            cfg, _, cam, _ = scenes.cornell_box_shortest(40, 32, max_bounces=5, seed=seed)
+        else:
+            cfg, _, cam, _ = scenes.cornell_box_v2(40, 32, max_bounces=5, seed=seed)      # plain marcher, rounded boxes (0.01)
+        cam.lookfrom = vec3(float(centre[0]), float(centre[1]), float(centre[2] + 3.5 * half))
+        cam.lookat = vec3(float(centre[0]), float(centre[1]), float(centre[2]))
+        L, src, cfg, objs_, cam = jit_hostcheck(f"room{seed}{family}", tmp_path_factory, scene=(cfg, objs, cam))
+        assert "#define RT_JIT_FAST 1" in src and "#define RT_JIT_BBOX 1" in src, src[:600]
+        arr, nobj = _native_objects(objs)
+        pts = (centre + rng.uniform(-1.3, 1.3, (30000, 3)) * half).astype(np.float32)
+        n_ok = C.c_int(0)
+        bad = L.hostcheck_jit_fast(C.byref(cfg), arr, nobj, 0, pts.ctypes.data_as(C.POINTER(C.c_float)), len(pts), C.byref(n_ok))
+        assert bad == 0 and n_ok.value > 3000, (bad, n_ok.value)
+        n = 6000
+        o = centre + rng.uniform(-1.0, 1.0, (n, 3)) * half * 0.95
+        o[: n // 3] = np.asarray(cam.lookfrom, np.float64)
+        d = rng.normal(size=(n, 3))
+        d[: n // 3] = np.asarray(cam.lookat, np.float64) - np.asarray(cam.lookfrom, np.float64) + rng.normal(size=(n // 3, 3)) * 0.3 * half
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays = np.concatenate([o, d], axis=1).astype(np.float32)
+        out = (C.c_int * 3)()
+        bad = L.hostcheck_jit_march(C.byref(cfg), arr, nobj, 0, rays.ctypes.data_as(C.POINTER(C.c_float)), n, out)
+        assert bad == 0
+        assert out[2] <= out[1]                                            # never more steps than the reference's march
 
 
 @pytest.mark.parametrize("name", list(PRESETS))
