@@ -33,7 +33,7 @@ extern "C" {
 #define RTPBR_API
 #endif
 
-#define RTPBR_VERSION 1
+#define RTPBR_VERSION 2
 #define RTPBR_MAX_OBJECTS 16
 #define RTPBR_MAX_BOUNCES 1024
 
@@ -120,6 +120,14 @@ typedef struct RtpbrConfig {
     int32_t adaptive_sampling;    /* ADAPTIVE_SAMPLING, src/config.py:14 (family C): pathtrace() skips pixels whose running
                                      mean of tone-mapped change, diff_pixels, is <= noise_threshold (src/pathtracer.py:97-101) */
     float noise_threshold;        /* NOISE_THRESHOLD, src/config.py:17 */
+    int32_t inner_spp;            /* > 0 (family B): kernel render() of examples/bunny/bunny_sdf.py:397-427 / bunny_sdf_v2.py:397-432 --
+                                     SAMPLE_PER_PIXEL samples per launch in an in-kernel loop that shares ONE ti.random stream per pixel;
+                                     every launch overwrites image_buffer with their sum.  Pixel-granular: runs on the one-thread-per-pixel
+                                     kernel (RTPBR_KERNEL_SIMPLE is implied) */
+    int32_t primary_miss;         /* a camera ray that misses everything: 0 colour *= sky (bunny_sdf_glass.py:355), 1 white
+                                     (bunny_sdf_v2.py:355-358), 2 colour *= 0, then *= sky (bunny_sdf.py:352-353) */
+    int32_t bunny_bob;            /* neural bunny animation: 1 rotation + bob 0.1 sin t (bunny_sdf_glass.py:213-216, v2), 0 rotation only
+                                     (bunny_sdf.py:214) */
     int32_t kernel;               /* RTPBR_KERNEL_* */
     int32_t count_work;           /* 1: count scene evals / rays / lane occupancy (slower) */
 } RtpbrConfig;

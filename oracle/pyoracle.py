@@ -57,6 +57,7 @@ class OrcConfig(C.Structure):
         ("black_background", C.c_int32),
         ("nearest_seed", C.c_int32), ("normal_mode", C.c_int32), ("samples_per_pixel", C.c_int32),
         ("adaptive_sampling", C.c_int32), ("noise_threshold", C.c_float),
+        ("inner_spp", C.c_int32), ("primary_miss", C.c_int32), ("bunny_bob", C.c_int32),
     ]
 
 

@@ -78,6 +78,7 @@ class RtpbrConfig(C.Structure):
         ("black_background", C.c_int32),
         ("nearest_seed", C.c_int32), ("normal_mode", C.c_int32), ("samples_per_pixel", C.c_int32),
         ("adaptive_sampling", C.c_int32), ("noise_threshold", C.c_float),
+        ("inner_spp", C.c_int32), ("primary_miss", C.c_int32), ("bunny_bob", C.c_int32),
         ("kernel", C.c_int32), ("count_work", C.c_int32),
     ]
 

@@ -152,6 +152,9 @@ int validate_config(const RtpbrConfig& c)
         return fail(RTPBR_ERR_UNSUPPORTED, "family C (src/) uses the src marcher and bsdf 2");
     if (c.family == RTPBR_FAMILY_C && c.samples_per_pixel < 1) return fail(RTPBR_ERR_ARG, "bad samples_per_pixel");
     if (c.sky < RTPBR_SKY_BLACK || c.sky > RTPBR_SKY_GRADIENT) return fail(RTPBR_ERR_ARG, "bad sky");
+    if (c.inner_spp < 0 || (c.inner_spp > 0 && c.family != RTPBR_FAMILY_B))
+        return fail(RTPBR_ERR_ARG, "inner_spp (in-kernel sample loop of bunny_sdf.py / bunny_sdf_v2.py) belongs to family B");
+    if (c.primary_miss < 0 || c.primary_miss > 2) return fail(RTPBR_ERR_ARG, "bad primary_miss");
     return RTPBR_OK;
 }
 
@@ -555,7 +558,7 @@ int rtpbr_pathtrace(RtpbrContext* c, int spp)
     }
     std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
     int rc;
-    if (c->cfg.kernel == RTPBR_KERNEL_SIMPLE) {
+    if (c->cfg.kernel == RTPBR_KERNEL_SIMPLE || c->cfg.inner_spp > 0) {   // (the in-kernel sample loop is pixel-granular)
         c->P.spp = spp;
         c->P.sample_base = c->sample_base;
         if ((rc = next_event_pair(c, &ev)) != RTPBR_OK) return rc;

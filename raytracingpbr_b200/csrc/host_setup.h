@@ -127,6 +127,9 @@ inline void fill_config(KParams& P, const RtpbrConfig& c)
     P.sky = c.sky; P.sky_scale = c.sky_scale;
     P.min_dis = c.min_dis; P.pixel_radius = c.pixel_radius; P.quality_per_sample = c.quality_per_sample;
     P.black_background = c.black_background;
+    P.inner_spp = c.inner_spp > 0 ? c.inner_spp : 0;
+    P.primary_miss = c.primary_miss;
+    P.bunny_bob = c.bunny_bob != 0;
 }
 
 // bunny_sdf_glass.py:213-216: t = pi * float(u_frame) / 120.0; angle(vec3(0, 0, t)); 0.1 * sin(t)

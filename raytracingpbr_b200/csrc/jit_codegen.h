@@ -319,7 +319,8 @@ struct Emitter {
                 break;
             case RTPBR_SHAPE_PLANE: dist[k] = "sd_plane(" + P_ + ", " + flit(o.scale[1]) + ")"; break;
             case RTPBR_SHAPE_BUNNY:
-                s += "    " + P_ + " = mat_mul(P.anim_m, " + P_ + ");\n    " + P_ + " = " + P_ + " + V3(0.0f, 0.0f, P.anim_bob);\n";
+                s += "    " + P_ + " = mat_mul(P.anim_m, " + P_ + ");\n";
+                if (cfg.bunny_bob) s += "    " + P_ + " = " + P_ + " + V3(0.0f, 0.0f, P.anim_bob);\n";
                 if (mode == -1) {
                     s += "    const float len" + K + " = length(" + P_ + ");\n    float hb" + K + " = len" + K + " - 0.8f;\n";
                     s += "    if (!(len" + K + " > 1.0f)) { need_mlp = true; pb = " + P_ + "; hb" + K + " = rt_inf(); }\n";

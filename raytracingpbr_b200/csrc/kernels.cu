@@ -28,6 +28,9 @@ __global__ void __launch_bounds__(kSimpleBlock) k_pathtrace_simple(const __grid_
     WorkCounters cnt = { 0, 0, 0, 0 };
     if (VAR::FAMILY == FAMILY_C) {
         trace_pixel_c<VAR>(P, pixel, i, j, acc, VAR::COUNT ? &cnt : nullptr);
+    } else if (VAR::FAMILY == FAMILY_B && P.inner_spp > 0) {
+        // P.spp launches of render(); every launch overwrites the buffer, so the last one is what remains
+        acc = trace_pixel_inner<VAR>(P, pixel, i, j, P.sample_base + (uint32_t)(P.spp - 1), VAR::COUNT ? &cnt : nullptr);
     } else {
         for (int s = 0; s < P.spp; ++s) {
             vec3 c = trace_sample<VAR>(P, pixel, i, j, P.sample_base + (uint32_t)s, VAR::COUNT ? &cnt : nullptr);

@@ -67,6 +67,9 @@ struct KParams {
     int32_t tiles_per_col;   // ceil(H / 8)
     int32_t nobj;
     int32_t resolve_min;     // pool kernel: resolve when this many slots are pending (or lanes would idle)
+    int32_t inner_spp;       // bunny_sdf.py / bunny_sdf_v2.py: in-kernel sample loop sharing one RNG stream (simple kernel only)
+    int32_t primary_miss;    // 0 x sky, 1 white, 2 x 0 x sky for camera rays that miss
+    int32_t bunny_bob;       // 1: the bunny's animation includes the bob
     int32_t count_mlp;       // count_work builds: count evaluations of the neural bunny's MLP (RTPBR_CNT_MLP_EVALS)
     DevCamera cam;
     DevGeom geom[kMaxObjects];

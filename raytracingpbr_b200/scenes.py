@@ -247,9 +247,40 @@ def bunny_glass(width: int = 1920, height: int = 1080, max_bounces: int = 512, s
     c.light_quality = 512.0                          # :33
     c.bsdf, c.f0_variant = 1, 0                      # :322
     c.sky = N.SKY_ENVMAP
+    c.bunny_bob = 1                                  # p += vec3(0, 0, 0.1*sin(t)) :215
     objects = [_obj(SHAPE_BUNNY, (0, 0, 0), (-90, 0, 0), (1, 1, 1), vec3(1, 1, 1) * 0.9, vec3(1), 0, 0, 1, 1.500)]   # :221-225
     camera = Camera(vec3(0, 0, 4), vec3(0, 0, 3), vec3(0, 1, 0), 30.0, width / height, 0.03, 4.0)     # :34-37, :435
     tonemap = dict(mode=1, exposure=0.8, gamma=2.2, frame=int(frame))  # :423-432; `frame`: u_frame (:409), applied by PathTracer
+    return c, objects, camera, tonemap
+
+
+def bunny_sdf_v2(width: int = 3840, height: int = 2160, max_bounces: int = 128, seed: int = 0, frame: int = 0, inner_spp: int = 12,
+                 kernel: int = N.KERNEL_PERSISTENT, count_work: bool = False):
+    """examples/bunny/bunny_sdf_v2.py (family B): the metal bunny on a white background.  Kernel render() traces
+    SAMPLE_PER_PIXEL samples per launch in an in-kernel loop that shares one ti.random stream per pixel and overwrites
+    image_buffer (:416-431): `pathtrace(n)` = n such launches.  Table for set_envmap: pow(texel * 1.8, 2.2) (:279-280)."""
+    c, _, _, _ = bunny_glass(width, height, max_bounces, seed, frame, kernel, count_work)
+    c.max_steps = 512                                # MAX_RAYMARCH :24
+    c.relax_w0, c.relax_guard, c.relax_reset, c.relax_w_reset = 1.6, 1, 0, 0.7     # :251, :257-258
+    c.light_quality = 128.0                          # :33
+    c.inner_spp = inner_spp                          # SAMPLE_PER_PIXEL :23, loop :419
+    c.primary_miss = 1                               # white background for camera rays :355-358
+    c.bunny_bob = 1                                  # :213-216
+    objects = [_obj(SHAPE_BUNNY, (0, 0, 0), (-90, 0, 0), (1, 1, 1), vec3(1, 1, 1) * 0.9, vec3(1), 0.0, 1, 0, 2.950)]   # :221-225
+    camera = Camera(vec3(0, 0, 4), vec3(0, 0, 3), vec3(0, 1, 0), 30.0, width / height, 0.01, 4.0)      # :34-37, :437
+    tonemap = dict(mode=1, exposure=0.8, gamma=2.2, frame=int(frame))      # :426-429 (exposure -> ACES -> gamma; the file does not clamp)
+    return c, objects, camera, tonemap
+
+
+def bunny_sdf(width: int = 3840, height: int = 2160, max_bounces: int = 128, seed: int = 0, frame: int = 0, inner_spp: int = 4,
+              kernel: int = N.KERNEL_PERSISTENT, count_work: bool = False):
+    """examples/bunny/bunny_sdf.py: like bunny_sdf_v2.py with SAMPLE_PER_PIXEL = 4, rotation without the bob (:214), camera
+    rays that miss are black (`ray.color *= sign(float(i))`, :352), Tokyo environment (x 1.8, ^2.2), camera at z = 5."""
+    c, objects, camera, tonemap = bunny_sdf_v2(width, height, max_bounces, seed, frame, inner_spp, kernel, count_work)
+    c.primary_miss = 2
+    c.bunny_bob = 0
+    camera = Camera(vec3(0, 0, 5), vec3(0, 0, 4), vec3(0, 1, 0), 30.0, width / height, 0.01, 4.0)      # :432
+    tonemap = dict(mode=1, exposure=0.6, gamma=2.2, frame=int(frame))      # camera_exposure :34
     return c, objects, camera, tonemap
 
 

@@ -144,6 +144,10 @@ def golden_case(name: str):
     elif name == "bunny_glass":
         cfg, objs, cam, tm = scenes.bunny_glass(W, H, max_bounces=int(g["bounces"]), seed=seed, frame=int(g["frame"]))
         env = env_table(g["env_u8"], 1.8, 2.2)                      # bunny_sdf_glass.py:279-280, applied per texel
+    elif name in ("bunny_sdf_v2", "bunny_sdf"):
+        preset = scenes.bunny_sdf_v2 if name == "bunny_sdf_v2" else scenes.bunny_sdf
+        cfg, objs, cam, tm = preset(W, H, max_bounces=int(g["bounces"]), seed=seed, frame=int(g["frame"]), inner_spp=int(g["inner_spp"]))
+        env = env_table(g["env_u8"], 1.8, 2.2)                      # bunny_sdf_v2.py:279-280
     elif name in ("src_scene", "src_adaptive"):
         cfg, objs, cam, tm = scenes.src_scene(W, H, seed=seed)
         env = env_table(g["env_u8"], 1.4, 2.2)                      # src/ibl.py:33

@@ -114,6 +114,8 @@ static void run(const KParams& P, float4* buf)
         float4 acc = buf[pixel];
         if (VAR::FAMILY == FAMILY_C) {
             trace_pixel_c<VAR>(P, pixel, i, j, acc, nullptr);
+        } else if (VAR::FAMILY == FAMILY_B && P.inner_spp > 0) {
+            acc = trace_pixel_inner<VAR>(P, pixel, i, j, P.sample_base + (uint32_t)(P.spp - 1), nullptr);
         } else {
             for (int s = 0; s < P.spp; ++s) {
                 vec3 c = trace_sample<VAR>(P, pixel, i, j, P.sample_base + (uint32_t)s, nullptr);

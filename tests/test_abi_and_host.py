@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     L = N.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.rtpbr_version() == 1
+    assert L.rtpbr_version() == 2        # RTPBR_VERSION: 2 = RtpbrConfig grew inner_spp / primary_miss / bunny_bob
 
 
 def test_struct_layouts_match_header():

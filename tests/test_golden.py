@@ -436,3 +436,51 @@ def test_cuda_family_c_matches_reference_source():
             pt.pathtrace(int(g["launches"]))
             assert np.array_equal(pt.image_buffer.to_numpy(), g["image_buffer"]), kernel
             assert np.array_equal(pt.ray_buffer.to_numpy().view(np.int32), g["ray_buffer"].view(np.int32)), kernel
+
+
+# ---------------------------------------------------------------- bunny_sdf.py / bunny_sdf_v2.py: in-kernel sample loop
+INNER = ["bunny_sdf_v2", "bunny_sdf"]
+
+
+@pytest.mark.parametrize("name", INNER)
+def test_oracle_inner_sample_loop_matches_reference_source(name):
+    """kernel render() of examples/bunny/bunny_sdf_v2.py:397-432 / bunny_sdf.py: SAMPLE_PER_PIXEL samples per launch on ONE
+    ti.random stream per pixel, image_buffer overwritten by every launch, white / black background for camera rays,
+    w = 1.6 -> 0.7 relaxation, metal bunny; bunny_sdf.py animates without the bob."""
+    g, oc, oo, env = oracle_of(name)
+    assert oc.inner_spp == int(g["inner_spp"]) and oc.primary_miss in (1, 2)
+    assert np.array_equal(po.pathtrace(oc, oo, 1, env=env), g["image_buffer_first"])
+    got = po.pathtrace(oc, oo, int(g["launches"]), env=env)
+    assert np.array_equal(got, g["image_buffer"])
+    assert (got[..., 3] == float(g["inner_spp"])).all()                        # overwritten, not accumulated
+    L = po.lib()
+    for p, row in zip(g["sd_points"], g["sd_values"]):                          # signed_distance incl. the animation (with / without bob)
+        assert np.float32(L.orc_signed_distance_g(C.byref(oc), oo, len(oo), 0, f32p(p))) == row[0]
+    if name == "bunny_sdf_v2":
+        assert (got[..., :3] == float(g["inner_spp"])).all(axis=-1).any()      # pure white background pixels exist
+
+
+@pytest.mark.parametrize("name", INNER)
+def test_product_host_code_inner_sample_loop_matches_reference_source(name):
+    g, cfg, objs, cam, tm, env = common.golden_case(name)
+    img = common.hostcheck_pathtrace(cfg, cam, objs, int(g["launches"]), env=env, frame=int(g["frame"]))
+    assert np.array_equal(img, g["image_buffer"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", INNER)
+def test_cuda_inner_sample_loop_matches_reference_source(name):
+    from raytracingpbr_b200 import PathTracer
+    g, cfg, objs, cam, tm, env = common.golden_case(name)
+    with PathTracer(cfg, objs, cam, tm) as pt:            # the preset's tonemap dict carries the frame
+        pt.set_envmap(env)
+        pt.refresh()
+        pt.pathtrace(1)
+        first = pt.image_buffer.to_numpy()
+        pt.pathtrace(int(g["launches"]) - 1)
+        buf = pt.image_buffer.to_numpy()
+        pt.post_process()
+        pix = pt.image_pixels.to_numpy()
+    assert np.array_equal(first, g["image_buffer_first"])
+    assert np.array_equal(buf, g["image_buffer"])
+    np.testing.assert_allclose(pix, np.clip(g["image_pixels"], 0.0, 1.0), atol=3e-5)     # (the file does not clamp; the kernel does)

@@ -431,6 +431,39 @@ def gen_bunny(name, width, height, bounces, spp, seed, frame):
     return out
 
 
+def gen_bunny_inner(name, script, width, height, bounces, inner, seed, frame, launches, camera_z):
+    """examples/bunny/bunny_sdf.py / bunny_sdf_v2.py: kernel render() with its in-kernel SAMPLE_PER_PIXEL loop (one ti.random
+    stream per pixel and launch, image_buffer overwritten by every launch), white / black camera-ray background."""
+    env_u8 = synthetic_env(seed=15)
+    ti.tools.imread = lambda path: env_u8
+    spp_line = {"bunny_sdf_v2": "SAMPLE_PER_PIXEL = 12", "bunny_sdf": "SAMPLE_PER_PIXEL = 4"}[script]
+    subs = [("image_resolution = (3840, 2160)", f"image_resolution = ({width}, {height})"),
+            ("MAX_RAYTRACE = 128", f"MAX_RAYTRACE = {bounces}"),
+            (spp_line, f"SAMPLE_PER_PIXEL = {inner}"),
+            ("while window.running:", "while False:")]
+    m = load_script(f"examples/bunny/{script}.py", f"ref_{script}_{name}", subs)
+    install_rng(seed)
+    out = {"width": width, "height": height, "bounces": bounces, "inner_spp": inner, "launches": launches, "seed": seed, "frame": frame,
+           "env_u8": env_u8, "lookfrom": np.array([0, 0, camera_z], np.float32), "lookat": np.array([0, 0, camera_z - 1], np.float32)}
+    rnd = np.random.default_rng(81)
+    pts = rnd.uniform(-0.7, 0.7, (16, 3)).astype(np.float32)
+    pts[:3] *= 2.5
+    m.u_frame[None] = frame
+    out["sd_points"] = pts
+    out["sd_values"] = np.array([[m.signed_distance(m.objects[0], vec3(*p.tolist()))] for p in pts], np.float32)
+    t0 = time.time()
+    bufs = []
+    for L in range(launches):
+        ti.rng.launch = L
+        m.render(vec3(0, 0, camera_z), vec3(0, 0, camera_z - 1), vec3(0, 1, 0), False, frame)
+        bufs.append(m.image_buffer.to_numpy())
+    out["image_buffer"] = bufs[-1]
+    out["image_buffer_first"] = bufs[0]
+    out["image_pixels"] = m.image_pixels.to_numpy()
+    print(f"  {name}: {width}x{height} x {inner} samples per launch x {launches} launches in {time.time() - t0:.1f} s")
+    return out
+
+
 class _SrcFinder:
     """Imports `src.*` from the reference tree, applying parameter substitutions to src/config.py."""
     def __init__(self, subs):
@@ -637,6 +670,9 @@ FIXTURES = {
     "tokyo_ibl": (gen_tokyo, dict(width=12, height=8, spp=3, seed=3)),
     "scene_demo": (gen_tokyo, dict(width=8, height=6, spp=2, seed=4, script="main")),
     "bunny_glass": (gen_bunny, dict(width=8, height=6, bounces=16, spp=1, seed=5, frame=7)),
+    # the two other bunny scripts: in-kernel sample loop on one RNG stream, white / black background for camera rays
+    "bunny_sdf_v2": (gen_bunny_inner, dict(script="bunny_sdf_v2", width=8, height=6, bounces=12, inner=3, seed=12, frame=5, launches=2, camera_z=4)),
+    "bunny_sdf": (gen_bunny_inner, dict(script="bunny_sdf", width=8, height=6, bounces=12, inner=2, seed=13, frame=9, launches=2, camera_z=5)),
     "src_scene": (gen_src, dict(width=10, height=6, launches=12, seed=6)),
     "src_adaptive": (gen_src, dict(width=8, height=6, launches=14, seed=8, adaptive=True, noise_threshold=0.2)),
 }
