@@ -295,7 +295,7 @@ def test_specialised_march_renders_the_same_image_on_host(name, tmp_path_factory
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("seed", [11, 12, 13])
+@pytest.mark.parametrize("seed", [11, 12])
 def test_scene_analyses_on_random_rooms(seed, tmp_path_factory):
     """The code generator's analyses on scenes nobody tuned: rooms made of axis-aligned slabs with random extents,
     offsets and quarter-turn rotations (so that the near-permutation matrices carry the reference's -4.4e-8 entries in
