@@ -169,7 +169,8 @@ enum : int { MODE_ALL = 0, MODE_HITS = 1, MODE_FRESH = 2 };
 template <class VAR, int NSLOT, int MODE = MODE_ALL>
 __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& pool, const int slot, const int lane,
                                               const unsigned lane_lt, uint8_t* ready, int& n_ready, volatile uint32_t* wq,
-                                              WorkCounters& cnt, uint8_t* pend = nullptr, int* n_pend = nullptr, uint8_t* fresh = nullptr)
+                                              WorkCounters& cnt, uint8_t* pend = nullptr, int* n_pend = nullptr, uint8_t* fresh = nullptr,
+                                              int* n_fresh = nullptr)
 {
     // ---- load the slot
     Path p;
@@ -337,8 +338,16 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
                 if (begun) p.m.t_stop = ray_t_stop<VAR>(P, p.m);
 #endif
 #if defined(RT_JIT_FAST)
-                const int pre = slow_march<VAR>(P, p.m);
-                st = pre == MARCH_CONTINUE ? ST_READY : (pre == MARCH_HIT ? ST_HIT : ST_MISS);
+                if (MODE == MODE_HITS) {
+                    // hit batches carry no full-code march steps: a bounce that begins outside the fast region (rare)
+                    // joins the slots that wait for a regeneration batch, where those steps are taken at full lanes
+                    bool ok;
+                    jit_nearest_fast(P, at(p.m.ro, p.m.rd, p.m.t), ok);
+                    if (!ok) st = ST_SLOW;
+                } else {
+                    const int pre = slow_march<VAR>(P, p.m);
+                    st = pre == MARCH_CONTINUE ? ST_READY : (pre == MARCH_HIT ? ST_HIT : ST_MISS);
+                }
 #endif
             }
         }
@@ -356,9 +365,9 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
     // ---- write the slot back; ready slots go on the ready stack
     if (slot >= 0) {
         pool.seti(F_STATUS, slot, st);
-        const bool marched_here = MODE == MODE_FRESH && (st == ST_HIT || st == ST_MISS);   // irregular new ray, marched by the generic code
+        const bool marched_here = MODE == MODE_FRESH && (st == ST_HIT || st == ST_MISS);   // marched right here (irregular ray, or full-code steps)
         if (marched_here) pool.setf(F_TEVAL, slot, p.m.t_eval);
-        if (st == ST_READY || marched_here) {
+        if (st == ST_READY || marched_here || (MODE == MODE_HITS && st == ST_SLOW)) {
             store_ready<VAR, NSLOT>(pool, slot, p.m);
             pool.setf(F_COLX, slot, p.col.x); pool.setf(F_COLY, slot, p.col.y); pool.setf(F_COLZ, slot, p.col.z);
             pool.seti(F_DEPTH, slot, p.depth);
@@ -378,12 +387,11 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
     const unsigned rdy = __ballot_sync(kFull, slot >= 0 && st == ST_READY);
     if (slot >= 0 && st == ST_READY) ready[n_ready + __popc(rdy & lane_lt)] = (uint8_t)slot;
     n_ready += __popc(rdy);
-    if (MODE == MODE_HITS) {          // ended paths: onto the fresh stack
-        const unsigned fr = __ballot_sync(kFull, slot >= 0 && st == ST_FETCH);
-        const int n_fresh = (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
-        if (slot >= 0 && st == ST_FETCH) fresh[n_fresh + __popc(fr & lane_lt)] = (uint8_t)slot;
-        __syncwarp();
-        if (lane == 0) wq[WQ_NFRESH] = (uint32_t)(n_fresh + __popc(fr));
+    if (MODE == MODE_HITS) {          // ended paths (and bounces that begin outside the fast region): onto the fresh stack
+        const bool to_fresh = slot >= 0 && (st == ST_FETCH || st == ST_SLOW);
+        const unsigned fr = __ballot_sync(kFull, to_fresh);
+        if (to_fresh) fresh[*n_fresh + __popc(fr & lane_lt)] = (uint8_t)slot;
+        *n_fresh += __popc(fr);
     }
     if (MODE == MODE_FRESH) {         // irregular new rays were marched right here: they need a hit / miss batch
         const unsigned hm = __ballot_sync(kFull, slot >= 0 && (st == ST_HIT || st == ST_MISS));
@@ -405,10 +413,10 @@ __device__ __forceinline__ void pool_body(const KParams& P)
     pool.w = smem + warp * kWarpWords;
     uint8_t* ready = reinterpret_cast<uint8_t*>(pool.w + F_COUNT * NSLOT);
     uint8_t* pend = ready + NSLOT;
-    uint8_t* fresh = pend + NSLOT;            // kRegen: slots waiting for a new path (count in wq[WQ_NFRESH])
+    uint8_t* fresh = pend + NSLOT;            // kRegen: slots waiting for a regeneration batch (a new path, or full-code march steps)
     volatile uint32_t* wq = pool.w + F_COUNT * NSLOT + kPoolStacks * (NSLOT / 4);   // the warp's chunk of the work queue
-    int n_ready = 0, n_pend = kRegen ? 0 : NSLOT;          // warp-uniform
-    if (lane < kPoolQueueWords) wq[lane] = (kRegen && lane == WQ_NFRESH) ? (uint32_t)NSLOT : 0u;
+    int n_ready = 0, n_pend = kRegen ? 0 : NSLOT, n_fresh = kRegen ? NSLOT : 0;          // warp-uniform
+    if (lane < kPoolQueueWords) wq[lane] = 0u;
 
     for (int s = lane; s < NSLOT; s += 32) {
         pool.seti(F_STATUS, s, ST_FETCH);
@@ -447,7 +455,6 @@ __device__ __forceinline__ void pool_body(const KParams& P)
         int n_wait = n_pend;          // slots the resolve phase could work on
         bool regen = false;           // warp-uniform: regeneration batches run in this round
         if (kRegen && active != kFull) {
-            const int n_fresh = (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
             regen = n_fresh > 0 && (n_fresh >= RT_REGEN_MIN || 32 - __popc(active) >= RT_REGEN_IDLE);
             if (regen) n_wait += n_fresh;
         }
@@ -482,19 +489,17 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                     const int slot = lane < take ? (int)pend[n_pend - 1 - lane] : -1;
                     n_pend -= take;
                     if (VAR::COUNT) c_resolved += (unsigned long long)take;
-                    resolve_batch<VAR, NSLOT, MODE_HITS>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt, pend, &n_pend, fresh);
+                    resolve_batch<VAR, NSLOT, MODE_HITS>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt, pend, &n_pend, fresh, &n_fresh);
                     if (n_pend < 32) break;
                 }
                 // regeneration: when enough slots wait for a new path, or when lanes would idle otherwise
                 for (;;) {
-                    const int n_fresh = (int)__shfl_sync(kFull, wq[WQ_NFRESH], 0);
                     if (n_fresh == 0 || !(regen || n_fresh >= RT_REGEN_MIN)) break;
                     const int take = min(n_fresh, 32);
                     const int slot = lane < take ? (int)fresh[n_fresh - 1 - lane] : -1;
+                    n_fresh -= take;
                     __syncwarp();
-                    if (lane == 0) wq[WQ_NFRESH] = (uint32_t)(n_fresh - take);
-                    __syncwarp();
-                    resolve_batch<VAR, NSLOT, MODE_FRESH>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt, pend, &n_pend, fresh);
+                    resolve_batch<VAR, NSLOT, MODE_FRESH>(P, pool, slot, lane, lane_lt, ready, n_ready, wq, cnt, pend, &n_pend, fresh, &n_fresh);
                     regen = false;                                // further batches only while they are well filled
                 }
             }
@@ -565,16 +570,26 @@ __device__ __forceinline__ void pool_body(const KParams& P)
         // pending stack and take a ready-to-march one straight away (no extra pass while the ready stack lasts)
         {
             const int nf = __popc(fin);
-            if ((fin >> lane) & 1u) {
-                const int r = __popc(fin & lane_lt);
+            const bool mine = (fin >> lane) & 1u;
 #if defined(RT_JIT_FAST)
-                if (march_undo_slow<VAR>(m, aux, slow)) {          // nothing was advanced: the slot keeps its march state and goes on in the resolve phase
+            const bool dropped = mine && march_undo_slow<VAR>(m, aux, slow);   // nothing was advanced: the march goes on in the resolve phase
+            // with regeneration batches the drop-outs wait for one of those (full-code steps at full lanes) instead of
+            // riding along in a hit batch
+            const unsigned drop_mask = kRegen ? __ballot_sync(kFull, dropped) : 0u;
+#else
+            const bool dropped = false;
+            const unsigned drop_mask = 0u;
+#endif
+            if (mine) {
+                const int r = __popc(fin & lane_lt);
+                if (dropped) {
                     store_parked<VAR, NSLOT>(pool, my, m);
                     pool.seti(F_STATUS, my, ST_SLOW);
-                } else
-#endif
-                store_finished<VAR, NSLOT>(pool, my, m, march_status<VAR>(P, aux) == MARCH_HIT ? ST_HIT : ST_MISS);
-                pend[n_pend + r] = (uint8_t)my;
+                } else {
+                    store_finished<VAR, NSLOT>(pool, my, m, march_status<VAR>(P, aux) == MARCH_HIT ? ST_HIT : ST_MISS);
+                }
+                if (kRegen && dropped) fresh[n_fresh + __popc(drop_mask & lane_lt)] = (uint8_t)my;
+                else pend[n_pend + __popc(fin & ~drop_mask & lane_lt)] = (uint8_t)my;
                 if (r < n_ready) {
                     my = ready[n_ready - 1 - r];
                     load_march<VAR, NSLOT>(pool, my, m);
@@ -583,7 +598,8 @@ __device__ __forceinline__ void pool_body(const KParams& P)
                     idle_march(m);
                 }
             }
-            n_pend += nf;
+            n_pend += nf - __popc(drop_mask);
+            n_fresh += __popc(drop_mask);
             if (nf <= n_ready) {
                 n_ready -= nf;
             } else {
