@@ -339,11 +339,9 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
 #endif
 #if defined(RT_JIT_FAST)
                 if (MODE == MODE_HITS) {
-                    // hit batches carry no full-code march steps: a bounce that begins outside the fast region (rare)
-                    // joins the slots that wait for a regeneration batch, where those steps are taken at full lanes
-                    bool ok;
-                    jit_nearest_fast(P, at(p.m.ro, p.m.rd, p.m.t), ok);
-                    if (!ok) st = ST_SLOW;
+                    // hit batches carry no full-code march steps and no region test: a bounce that begins outside the
+                    // fast region (rare: bounces start on surfaces inside it) drops out of the march loop at its first
+                    // step and then waits for a regeneration batch like every other drop-out
                 } else {
                     const int pre = slow_march<VAR>(P, p.m);
                     st = pre == MARCH_CONTINUE ? ST_READY : (pre == MARCH_HIT ? ST_HIT : ST_MISS);
