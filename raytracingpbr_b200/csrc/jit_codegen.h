@@ -361,12 +361,18 @@ struct Emitter {
         s += "    return 0.5f * best;\n}\n";
     }
 
-    // jit_nearest_fast: walls as planes inside the fast region, everything else as in jit_nearest_dist
-    void emit_fast(const Analysis& A)
+    // jit_nearest_fast: walls as planes inside the fast region, everything else as in jit_nearest_dist.
+    // with_index: jit_nearest_fast_idx, the argmin as well (same compare chain as jit_nearest: object order, strict '<')
+    void emit_fast(const Analysis& A, bool with_index = false)
     {
         static const char* axes[3] = { "x", "y", "z" };
-        s += "// ok: pos lies in the fast region and outside every wall's slab; then the result has the bits of jit_nearest_dist(pos)\n";
-        s += "RT_HD float jit_nearest_fast(const KParams& P, vec3 pos, bool& ok)\n{\n";
+        if (!with_index) {
+            s += "// ok: pos lies in the fast region and outside every wall's slab; then the result has the bits of jit_nearest_dist(pos)\n";
+            s += "RT_HD float jit_nearest_fast(const KParams& P, vec3 pos, bool& ok)\n{\n";
+        } else {
+            s += "// ... and this one the bits and the index of jit_nearest(pos, index)\n";
+            s += "RT_HD float jit_nearest_fast_idx(const KParams& P, vec3 pos, bool& ok, int& index)\n{\n";
+        }
         std::string in;
         for (int a = 0; a < 3; ++a) {
             const std::string e = A.rc[a] == 0.0f ? std::string("fabsf(pos.") + axes[a] + ")"
@@ -402,6 +408,25 @@ struct Emitter {
         std::vector<bool> doubled(n, false);
         for (int k : rest) emit_point(k);
         emit_distances(rest, 2, dist, doubled);
+        if (with_index) {
+            // doubled distances of ALL objects in object order: the compare chain of jit_nearest
+            s += "    float best = " + flit(2.0f * cfg.t_far) + ";\n    int idx = 0;\n";
+            for (int k = 0; k < n; ++k) {
+                const std::string K = idx(k);
+                if (is_wall[k]) {
+                    const std::string g = round_ != 0.0f ? "g" + K : "fabsf(q" + K + ")";
+                    s += "    const float a" + K + " = " + g + " + " + g + ";\n";
+                } else if (doubled[k]) {
+                    s += "    const float a" + K + " = fabsf(" + dist[k] + ");\n";
+                } else {
+                    s += "    const float h" + K + " = " + dist[k] + ";\n    const float a" + K + " = fabsf(h" + K + " + h" + K + ");\n";
+                }
+                if (k == 0 && cfg.nearest_seed == 0) s += "    best = a0;\n";
+                else s += "    if (a" + K + " < best) { best = a" + K + "; idx = " + K + "; }\n";
+            }
+            s += "    index = idx;\n    return 0.5f * best;\n}\n";
+            return;
+        }
         std::string best;
         if (cfg.nearest_seed != 0) best = flit(2.0f * cfg.t_far);
         for (int k : rest) {
@@ -469,7 +494,7 @@ inline Source generate(const RtpbrConfig& cfg, const RtpbrObject* objs, int n, i
     E.emit_full(1);
     E.emit_full(0);
     if (split) E.emit_full(-1);
-    if (A.fast) E.emit_fast(A);
+    if (A.fast) { E.emit_fast(A); E.emit_fast(A, true); }
     s += "}  // namespace rt\n\n";
     const std::string variant = std::string("rt::Variant<rt::") + family + ", 0, rt::" + shapeset + ", rt::" + marcher + ", false>";
     s += "extern \"C\" __global__ void __launch_bounds__(rt::kPoolBlock, rt::PoolLaunch<" + variant + ">::kMinBlocks)\n"

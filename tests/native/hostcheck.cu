@@ -91,9 +91,14 @@ HC_API int hostcheck_jit_fast(const RtpbrConfig* cfg, const RtpbrObject* objs, i
         const vec3 p = V3(pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]);
         bool ok;
         const float f = jit_nearest_fast(P, p, ok), d = jit_nearest_dist(P, p);
+        bool ok2;
+        int i_fast = -1, i_full = -2;
+        const float f2 = jit_nearest_fast_idx(P, p, ok2, i_fast), d2 = jit_nearest(P, p, i_full);
+        if (ok != ok2) ++bad;
         if (!ok) continue;
         ++*n_ok;
         if (memcmp(&f, &d, 4) != 0) ++bad;
+        if (memcmp(&f2, &d2, 4) != 0 || i_fast != i_full) ++bad;      // the argmin form: bits and index of jit_nearest()
     }
     return bad;
 #else
