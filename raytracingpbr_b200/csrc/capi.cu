@@ -379,8 +379,9 @@ int rtpbr_refresh(RtpbrContext* c)
 }
 
 // Pool geometry and scheduling policy of an NVRTC build.  Environment knobs win; otherwise kernels with a fast region
-// (family A: short march step, small resolve phase) run 3 CTAs/SM x 80 slots per warp, regenerate paths in batches of
-// their own and leave the march loop only when 6 lanes have finished (profiles/r02_sweeps.md); everything else keeps
+// (family A: short march step, small resolve phase) run 3 CTAs/SM x 88 slots per warp, regenerate paths (and continue
+// rays that dropped out of the region) in batches of their own and leave the march loop only when 6 lanes have finished
+// (profiles/r02_sweeps.md); everything else keeps
 // the ahead-of-time geometry.
 struct JitBuild {
     int block, slots, min_blocks;
@@ -395,12 +396,12 @@ static JitBuild jit_build_options(const rt::jit::Source& src)
         return x >= lo && x <= hi ? x : dflt;
     };
     JitBuild b;
-    b.slots = env_int("RTPBR_POOL_SLOTS", 32, 128, src.fast ? 80 : rt::kPoolSlots);
+    b.slots = env_int("RTPBR_POOL_SLOTS", 32, 128, src.fast ? 88 : rt::kPoolSlots);   // 3 x 75.6 KB: the most that fits 3 CTAs/SM
     if (b.slots % 4 != 0) b.slots = rt::kPoolSlots;
     b.block = env_int("RTPBR_POOL_BLOCK", 32, 1024, rt::kPoolBlock);
     if (b.block % 32 != 0) b.block = rt::kPoolBlock;
     b.min_blocks = env_int("RTPBR_POOL_MIN_BLOCKS", 1, 16, src.fast ? 3 : rt::kPoolMinBlocks);
-    const int regen_min = env_int("RTPBR_REGEN_MIN", 0, 32, src.fast ? 24 : 0);
+    const int regen_min = env_int("RTPBR_REGEN_MIN", 0, 32, src.fast ? 28 : 0);
     const int regen_idle = env_int("RTPBR_REGEN_IDLE", 1, 32, src.fast ? 8 : 1);
     const int fin_min = env_int("RTPBR_FIN_MIN", 1, 32, src.fast ? 6 : 1);
     b.defs = { "-DRT_POOL_BLOCK=" + std::to_string(b.block), "-DRT_POOL_SLOTS=" + std::to_string(b.slots),
