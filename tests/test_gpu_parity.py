@@ -334,3 +334,101 @@ def test_denoise_pass_equals_the_oracle_bit_for_bit():
         pt.refresh(); pt.pathtrace(2); pt.post_process(); pt.denoise(1e-3)
         a, b = pt.image_pixels.to_numpy(), pt.denoise_pixels.to_numpy()
         assert np.nanmax(b) <= a.max() + 1e-6
+
+
+def test_single_device_multi_path_tracer_equals_path_tracer():
+    """rtpbr_multi_* with one device: no communicator, same bits as the plain context (runs on 1-GPU boxes too)."""
+    from raytracingpbr_b200 import MultiPathTracer
+    cfg, objs, cam, tm = scenes.cornell_box_shortest(96, 64, max_bounces=5, seed=4)
+    with MultiPathTracer(cfg, objs, cam, tm, devices=[0]) as mpt:
+        mpt.render(3)
+        a, pa = mpt.image_buffer.to_numpy(), mpt.image_pixels.to_numpy()
+        mpt.pathtrace(2)                                     # one rank: nothing was reduced, accumulation goes on
+        b = mpt.image_buffer.to_numpy()
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.refresh(); pt.pathtrace(3); pt.post_process()
+        assert np.array_equal(pt.image_buffer.to_numpy(), a) and np.array_equal(pt.image_pixels.to_numpy(), pa)
+        pt.pathtrace(2)
+        assert np.array_equal(pt.image_buffer.to_numpy(), b)
+
+
+def test_sharded_context_without_a_communicator_refuses_to_reduce():
+    cfg, objs, cam, tm = scenes.cornell_box_shortest(64, 32, max_bounces=3, seed=1)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.set_shard(1, 4, 4)
+        pt.refresh(); pt.pathtrace(1)
+        with pytest.raises(RtpbrError) as e:
+            pt.reduce_tiles(0)
+        assert e.value.code == N.ERR_STATE and "rtpbr_nccl_init" in str(e.value)
+        pt.set_shard(0, 1, 4)
+        pt.reduce_tiles(0)                                   # one rank owns every column: nothing to do
+
+
+def test_unchanged_geometry_keeps_the_specialised_kernel_and_animation_falls_back():
+    """rtpbr_set_scene with the same geometry (or new materials only) must not rebuild / reload the kernel; a
+    scene whose geometry changes every launch renders through the ahead-of-time kernel (same bits) instead of paying an
+    NVRTC compile per frame, and the specialised kernel returns once the geometry is stable."""
+    import copy
+    import time
+    cfg, objs, cam, tm = scenes.cornell_box_shortest(64, 48, max_bounces=4, seed=9)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.refresh(); pt.pathtrace(1); pt.sync()
+        active, msg = pt.ctx.jit_status()
+        if not active and "dlopen" in msg:
+            pytest.skip("NVRTC not available: " + msg)
+        assert active
+        first = pt.image_buffer.to_numpy()
+        t0 = time.perf_counter()
+        for _ in range(20):                                  # same scene again and again: no rebuild (20 compiles would take ~40 s)
+            pt.set_scene(objs)
+            pt.refresh(); pt.ctx.set_sample_base(0); pt.pathtrace(1)
+        pt.sync()
+        assert time.perf_counter() - t0 < 5.0
+        assert pt.ctx.jit_status() == (True, msg)
+        assert np.array_equal(pt.image_buffer.to_numpy(), first)
+        recoloured = copy.deepcopy(objs)
+        recoloured[3].material.albedo = recoloured[4].material.albedo      # materials live in the parameter block
+        pt.set_scene(recoloured)
+        pt.refresh(); pt.ctx.set_sample_base(0); pt.pathtrace(1); pt.sync()
+        assert pt.ctx.jit_status()[0] and not np.array_equal(pt.image_buffer.to_numpy(), first)
+        # animation: the small box moves a little every launch
+        fell_back, want = False, None
+        for k in range(12):
+            moved = copy.deepcopy(objs)
+            moved[6].transform.position[0] = np.float32(0.275 + 0.001 * (k + 1))
+            pt.set_scene(moved)
+            pt.refresh(); pt.ctx.set_sample_base(0); pt.pathtrace(1); pt.sync()
+            active, m2 = pt.ctx.jit_status()
+            fell_back = fell_back or (not active and "ahead-of-time" in m2)
+        assert fell_back
+        got = pt.image_buffer.to_numpy()
+        oc, oo = common.to_oracle(cfg, cam, moved)
+        assert np.array_equal(got, po.pathtrace(oc, oo, 1))                # whichever kernel rendered it: the oracle's bits
+        for _ in range(40):                                  # geometry stable again: the specialised kernel comes back
+            pt.refresh(); pt.ctx.set_sample_base(0); pt.pathtrace(1)
+        pt.sync()
+        assert pt.ctx.jit_status()[0]
+        assert np.array_equal(pt.image_buffer.to_numpy(), got)
+
+
+def test_scene_with_two_neural_bunnies_jit_equals_aot():
+    """the two-stage (split) march keeps ONE pending MLP point, so scenes with more than one bunny use the
+    unsplit form; specialised and ahead-of-time kernels must agree."""
+    import copy
+    cfg, objs, cam, tm = scenes.bunny_glass(72, 48, max_bounces=6, seed=3)
+    second = copy.deepcopy(objs[0])
+    second.transform.position[0] = np.float32(0.9)
+    objs[0].transform.position[0] = np.float32(-0.6)
+    scene = [objs[0], second]
+    src = N.jit_source(cfg, [o.to_native() for o in scene])
+    assert "RT_JIT_SPLIT_BUNNY" not in src
+    env = _synthetic_env(seed=4)
+    out = {}
+    for jit in (True, False):
+        with PathTracer(cfg, scene, cam, tm) as pt:
+            pt.ctx.set_jit(jit)
+            pt.set_envmap(env)
+            pt.refresh(); pt.pathtrace(3)
+            out[jit] = pt.image_buffer.to_numpy()
+    assert np.array_equal(out[True], out[False])
+    assert (out[True][..., :3].sum(-1) > 0).mean() > 0.5
