@@ -38,6 +38,18 @@ constexpr unsigned kFull = 0xffffffffu;
 // runs on compacted batches.  The RNG is keyed by (pixel, sample, draw index) only, so the
 // scheduling cannot change any number a sample sees: results are bit-identical to the simple
 // kernel and to the CPU oracle.
+//
+// Round 2 (scene-specialised builds, switched on by the code generator / capi.cu: jit_build_options):
+//   RT_JIT_FAST   the march loop evaluates jit_nearest_fast() (walls as planes inside a proven region).  A lane whose
+//                 point lies outside the region "finishes" with status ST_SLOW, its step taken back; the full-code
+//                 steps it needs are taken by slow_march() in the resolve phase.
+//   RT_JIT_TSTOP  per-ray t_stop (slot word F_TSTOP): beyond it the ray provably misses (ray_t_stop).
+//   RT_REGEN_MIN  RESOLVE splits into two batch types.  MODE_HITS batches shade hits / misses and start the next bounce:
+//                 no work-queue pulls, no new paths, no full-code march steps.  MODE_FRESH ("regeneration") batches
+//                 take the slots of the third stack, `fresh`: ended paths (fetch + camera ray + first roulette + the
+//                 camera ray's full-code steps towards the region) and ST_SLOW drop-outs.  They run when RT_REGEN_MIN
+//                 slots wait or RT_REGEN_IDLE lanes have nothing to march.
+//   RT_FIN_MIN    finished lanes wait (masked) until RT_FIN_MIN of them can leave the march loop together.
 // ------------------------------------------------------------------------------------------
 enum : int { ST_NONE = 0, ST_READY = 1, ST_HIT = 2, ST_MISS = 3, ST_DONE = 4, ST_FETCH = 5, ST_NEWPATH = 6,
              ST_ADVANCE = 7, ST_DEAD = 8, ST_SLOW = 9 };
