@@ -432,3 +432,31 @@ def test_scene_with_two_neural_bunnies_jit_equals_aot():
             out[jit] = pt.image_buffer.to_numpy()
     assert np.array_equal(out[True], out[False])
     assert (out[True][..., :3].sum(-1) > 0).mean() > 0.5
+
+
+@pytest.mark.parametrize("w,h,spp,bounces", [(1, 1, 1, 1), (1, 1, 5, 8), (5, 3, 1, 3), (33, 17, 2, 8), (3, 70, 3, 2), (130, 2, 1, 8)])
+def test_tiny_and_ragged_images_fast_region_kernel(w, h, spp, bounces):
+    """Fewer work items than pool slots, single pixels, ragged tiles: the regeneration / finish-threshold scheduling must
+    drain cleanly (no hang) and give the oracle's bits."""
+    cfg, objs, cam, tm = scenes.cornell_box_shortest(w, h, max_bounces=bounces, seed=21)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.refresh()
+        pt.pathtrace(spp)
+        got = pt.image_buffer.to_numpy()
+        active, msg = pt.ctx.jit_status()
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    assert np.array_equal(got, po.pathtrace(oc, oo, spp)), (msg,)
+
+
+def test_shard_that_owns_no_columns_is_a_no_op():
+    cfg, objs, cam, tm = scenes.cornell_box_shortest(6, 9, max_bounces=4, seed=2)
+    with PathTracer(cfg, objs, cam, tm) as pt:
+        pt.set_shard(3, 4, 4)                                # columns 0..5 belong to ranks 0 and 1 only
+        pt.refresh(); pt.pathtrace(2)
+        assert not pt.image_buffer.to_numpy().any()
+        pt.set_shard(1, 4, 4)
+        pt.refresh(); pt.ctx.set_sample_base(0); pt.pathtrace(2)
+        part = pt.image_buffer.to_numpy()
+    oc, oo = common.to_oracle(cfg, cam, objs)
+    want = po.pathtrace(oc, oo, 2)
+    assert np.array_equal(part[4:6], want[4:6]) and not part[:4].any()
