@@ -22,6 +22,7 @@ What one JSON line carries
   c4            BASELINE configs[4]: 4096^2 x 1024 spp, 8 bounces, tile-sharded over the N ranks (strong); one timed step.
   workloads     (N = 1) configs[2] (bunny_sdf_glass 1024^2 x 256 spp x 16 bounces) and configs[3] (tokyo_ibl 1920 x 1080 x
                 128 spp x 8 bounces): Msamples/s, kernel ms and the counted-work fraction of the FP32 peak.
+  without_scene_analyses  (N = 1) the same step with the code generator's two exact shortcuts switched off, for transparency.
   roofline      the roof that bounds this path: FP32 instruction issue.  achieved = ALGORITHMIC flops (SURVEY.md 8(d):
                 41 flop per box SDF etc. x the reference algorithm's evaluation counts, counted by the counting twin of
                 the kernel) / the kernel's average launch duration (CUDA events on its launch stream).
@@ -669,6 +670,29 @@ def main() -> int:
             for name in ("c2", "c3"):
                 workloads[name] = run_extra(name, 2 if name == "c2" else 3, 1, R.local, sm_max_mhz)
 
+    # ---- transparency: the same step with both scene analyses off (N = 1) ---------------
+    plain = None
+    if world == 1 and rank == 0 and not args.no_blocks and kernel == N.KERNEL_PERSISTENT:
+        saved = {k: os.environ.get(k) for k in ("RTPBR_JIT_FAST", "RTPBR_JIT_BBOX")}
+        os.environ.update(RTPBR_JIT_FAST="0", RTPBR_JIT_BBOX="0")          # read when the specialised kernel is built
+        try:
+            pt2, _, _, _ = sharded_tracer(R, W, H, kernel)
+            t2 = timed_steps(R, pt2, SPP, 3, 3)
+            crc2, _ = image_crc(R, pt2, SPP)
+            jit2 = pt2.ctx.jit_status()[1]
+            pt2.close()
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        plain = {"value": float(W) * H * SPP / (t2["ms_per_step"] * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": t2["ms_per_step"], "steps": 3,
+                 "warmup": 3, "image_crc32": crc2, "jit": jit2,
+                 "note": "RTPBR_JIT_FAST=0 RTPBR_JIT_BBOX=0: every scene evaluation of the reference's march is executed with the full box "
+                         "formulas and missed rays are marched to t > MAX_DIS (the round-1 kernel); the headline kernel reaches the same "
+                         "image (same crc) through two exact shortcuts: walls as planes inside a proven region, provable misses cut short"}
+
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -702,6 +726,8 @@ def main() -> int:
             line["c4"] = c4
         if workloads:
             line["workloads"] = workloads
+        if plain:
+            line["without_scene_analyses"] = plain
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
