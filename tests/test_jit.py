@@ -167,7 +167,7 @@ def test_specialised_source_carries_the_right_variant_switches():
     a, cfg = src_of(scenes.cornell_box_shortest)
     assert "#define RT_K_MAX_STEPS %d\n" % cfg.max_steps in a and "#define RT_K_HIT_EPS" in a and "#define RT_K_T_FAR" in a
     assert "RT_RESOLVE_OOL" not in a and "RT_JIT_SPLIT_BUNNY" not in a and "jit_nearest_partial" not in a
-    assert a.count("sd_box2_ranged_x2<false>") == 9                      # 4 packed pairs x (jit_nearest, jit_nearest_dist) + 1 in jit_nearest_fast
+    assert a.count("sd_box2_ranged_x2<false>") == 10                     # 4 packed pairs x (jit_nearest, jit_nearest_dist) + 1 each in jit_nearest_fast / _fast_idx
     assert "#define RT_JIT_FAST 1" in a and "#define RT_JIT_BBOX 1" in a  # five walls as planes; bounded scene
     for preset in (scenes.tokyo_ibl, scenes.cornell_box, scenes.cornell_box_v3, scenes.src_scene):
         b, _ = src_of(preset)
