@@ -17,7 +17,7 @@ import common
 from oracle import pyoracle as po
 from raytracingpbr_b200 import ibl, scenes
 
-ASSET_DIRS = [os.environ.get("RTPBR_ASSETS"), os.path.join(common.ROOT, "tests", "assets_local"), "/root/reference/assets"]
+ASSET_DIRS = [os.environ.get("RTPBR_ASSETS"), os.path.join(common.ROOT, "tests", "assets_local")]   # staged by __graft_entry__.build()
 FILES = {"tokyo": "Tokyo_BigSight_3k.hdr", "limpopo": "limpopo_golf_course_3k.hdr"}
 
 
