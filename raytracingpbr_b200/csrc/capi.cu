@@ -400,7 +400,9 @@ static JitBuild jit_build_options(const rt::jit::Source& src)
     if (b.slots % 4 != 0) b.slots = rt::kPoolSlots;
     b.block = env_int("RTPBR_POOL_BLOCK", 32, 1024, rt::kPoolBlock);
     if (b.block % 32 != 0) b.block = rt::kPoolBlock;
-    b.min_blocks = env_int("RTPBR_POOL_MIN_BLOCKS", 1, 16, src.fast ? 3 : rt::kPoolMinBlocks);
+    // 3 CTAs/SM (<= 85 registers): the fast-region kernels, and the over-relaxed marchers, whose w / s / d state spills at
+    // 64 registers (tokyo_ibl +4.6 %, scene_demo +6 %, cornell_box_v3 +3.9 %, src +0.9 %; plain PBR marcher -1 %: stays at 4)
+    b.min_blocks = env_int("RTPBR_POOL_MIN_BLOCKS", 1, 16, (src.fast || src.relaxed) ? 3 : rt::kPoolMinBlocks);
     const int regen_min = env_int("RTPBR_REGEN_MIN", 0, 32, src.fast ? 28 : 0);
     const int regen_idle = env_int("RTPBR_REGEN_IDLE", 1, 32, src.fast ? 8 : 1);
     const int fin_min = env_int("RTPBR_FIN_MIN", 1, 32, src.fast ? 6 : 1);

@@ -71,6 +71,7 @@ struct Source {
     std::string kernel_name;
     bool fast = false;     // jit_nearest_fast() + drop-out handling are compiled in (RT_JIT_FAST)
     bool tstop = false;    // per-ray t_stop in the march loop (RT_JIT_TSTOP)
+    bool relaxed = false;  // over-relaxed marcher (enhanced / src) without the neural bunny: its march state wants > 64 registers
 };
 
 // Tuning / test knobs: unset = automatic, "0" = off, anything else = on wherever the analysis permits.
@@ -505,6 +506,7 @@ inline Source generate(const RtpbrConfig& cfg, const RtpbrObject* objs, int n, i
     out.kernel_name = "k_pathtrace_pool_jit";
     out.fast = A.fast;
     out.tstop = tstop;
+    out.relaxed = cfg.marcher != RTPBR_MARCH_PLAIN && !bunny;
     return out;
 }
 
