@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/rtpbr.h"
@@ -471,6 +472,19 @@ inline Source generate(const RtpbrConfig& cfg, const RtpbrObject* objs, int n, i
     // march-loop constants as literals (same values as the parameter block => same comparisons)
     s += "#define RT_K_HIT_EPS " + flit(cfg.hit_eps) + "\n#define RT_K_T_FAR " + flit(cfg.t_far) + "\n#define RT_K_MAX_STEPS " +
          std::to_string(cfg.max_steps) + "\n";
+    // configuration constants as literals (RT_CFG, rt_integrator.cuh): same values as fill_config() puts into the parameter block
+    s += "#define RT_K_CFG 1\n";
+    {
+        const std::pair<const char*, int> ints[] = {
+            { "bsdf", cfg.bsdf }, { "f0_variant", cfg.f0_variant }, { "normal_mode", cfg.normal_mode }, { "sky", cfg.sky },
+            { "relax_guard", cfg.relax_guard }, { "relax_reset", cfg.relax_reset }, { "black_background", cfg.black_background },
+            { "primary_miss", cfg.primary_miss }, { "bunny_bob", cfg.bunny_bob != 0 }, { "max_bounces", cfg.max_bounces } };
+        for (const auto& kv : ints) s += std::string("#define RT_K_") + kv.first + " " + std::to_string(kv.second) + "\n";
+        const std::pair<const char*, float> floats[] = {
+            { "relax_w_reset", cfg.relax_w_reset }, { "relax_w0", cfg.relax_w0 }, { "t_start", cfg.t_start }, { "normal_h", cfg.normal_h },
+            { "min_dis", cfg.min_dis }, { "visibility_min", cfg.visibility_min }, { "sky_scale", cfg.sky_scale }, { "box_round", cfg.box_round } };
+        for (const auto& kv : floats) s += std::string("#define RT_K_") + kv.first + " " + flit(kv.second) + "\n";
+    }
     if (A.bounded) {
         // world box around every surface; margin: see ray_t_stop() (rt_integrator.cuh)
         s += "#define RT_JIT_BBOX 1\n";
