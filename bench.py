@@ -498,6 +498,9 @@ def strong_job(R: Ranks, width: int, height: int, spp: int, warmup: int, steps: 
     """A FIXED width x height x spp job split over the ranks (BASELINE's multi-GPU case).  Rank 0 gets the dict."""
     pt, objs, cam, tm = sharded_tracer(R, width, height, kernel)
     try:
+        pt.refresh()                     # untimed 1 spp pass: the specialised kernel of this resolution is built (NVRTC, ~2 s) and
+        pt.pathtrace(1)                  # the scratch buffer allocated before the clock starts, whatever `warmup` is
+        pt.sync()
         t = timed_steps(R, pt, spp, warmup, steps)
         red = reduce_alone_ms(R, pt, spp)
         if width * height * spp <= (1 << 28):

@@ -478,12 +478,17 @@ inline Source generate(const RtpbrConfig& cfg, const RtpbrObject* objs, int n, i
         const std::pair<const char*, int> ints[] = {
             { "bsdf", cfg.bsdf }, { "f0_variant", cfg.f0_variant }, { "normal_mode", cfg.normal_mode }, { "sky", cfg.sky },
             { "relax_guard", cfg.relax_guard }, { "relax_reset", cfg.relax_reset }, { "black_background", cfg.black_background },
-            { "primary_miss", cfg.primary_miss }, { "bunny_bob", cfg.bunny_bob != 0 }, { "max_bounces", cfg.max_bounces } };
+            { "primary_miss", cfg.primary_miss }, { "bunny_bob", cfg.bunny_bob != 0 }, { "max_bounces", cfg.max_bounces },
+            { "samples_per_pixel", cfg.samples_per_pixel > 0 ? cfg.samples_per_pixel : 1 }, { "width", cfg.width }, { "height", cfg.height },
+            { "tiles_per_col", (cfg.height + 7) / 8 } };       // (fill_shard: work items are 4 x 8 tiles)
         for (const auto& kv : ints) s += std::string("#define RT_K_") + kv.first + " " + std::to_string(kv.second) + "\n";
         const std::pair<const char*, float> floats[] = {
             { "relax_w_reset", cfg.relax_w_reset }, { "relax_w0", cfg.relax_w0 }, { "t_start", cfg.t_start }, { "normal_h", cfg.normal_h },
-            { "min_dis", cfg.min_dis }, { "visibility_min", cfg.visibility_min }, { "sky_scale", cfg.sky_scale }, { "box_round", cfg.box_round } };
-        for (const auto& kv : floats) s += std::string("#define RT_K_") + kv.first + " " + flit(kv.second) + "\n";
+            { "min_dis", cfg.min_dis }, { "visibility_min", cfg.visibility_min }, { "sky_scale", cfg.sky_scale }, { "box_round", cfg.box_round },
+            { "pixel_radius", cfg.pixel_radius }, { "quality_per_sample", cfg.quality_per_sample },
+            { "inv_max_bounces", (float)(1.0 / (double)cfg.max_bounces) }, { "visibility_max", cfg.visibility_max } };
+        for (const auto& kv : floats)
+            s += std::string("#define RT_K_") + kv.first + " " + (std::isinf(kv.second) ? (kv.second > 0 ? "rt::rt_inf()" : "(-rt::rt_inf())") : flit(kv.second)) + "\n";
     }
     if (A.bounded) {
         // world box around every surface; margin: see ray_t_stop() (rt_integrator.cuh)

@@ -214,7 +214,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
             wid = (unsigned long long)(uint32_t)pool.geti(F_ACCX, slot) |
                   ((unsigned long long)(uint32_t)pool.geti(F_ACCY, slot) << 32);
     }
-    int pi = (int)(pixel / (uint32_t)P.height), pj = (int)(pixel - (uint32_t)pi * (uint32_t)P.height);
+    int pi = (int)(pixel / (uint32_t)RT_CFG(P, height)), pj = (int)(pixel - (uint32_t)pi * (uint32_t)RT_CFG(P, height));
 
     // ---- run the slot's state machine until it needs marching again (or dies)
     for (;;) {
@@ -312,8 +312,8 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
                 if (VAR::FAMILY == FAMILY_C) {          // work item = pixel
                     if (work_to_pixel(P, (uint32_t)wk, pi, pj) &&
                         // src/pathtracer.py:97-101: if diff > NOISE_THRESHOLD: sample(i, j)
-                        (!P.adaptive || P.diff_pixels[pi * P.height + pj] > P.noise_threshold)) {
-                        pixel = (uint32_t)(pi * P.height + pj);
+                        (!P.adaptive || P.diff_pixels[pi * RT_CFG(P, height) + pj] > P.noise_threshold)) {
+                        pixel = (uint32_t)(pi * RT_CFG(P, height) + pj);
                         acc = P.image_buffer[pixel];
                         samp = 0;
                         k = 0;
@@ -324,7 +324,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
                 } else {                                // work item = (pixel item, sample)
                     const uint32_t s1 = samp0 + r, q1 = s1 / (uint32_t)P.spp;
                     if (work_to_pixel(P, item0 + q1, pi, pj)) {
-                        pixel = (uint32_t)(pi * P.height + pj);
+                        pixel = (uint32_t)(pi * RT_CFG(P, height) + pj);
                         samp = (int)(s1 - q1 * (uint32_t)P.spp);
                         wid = wk;
                         st = ST_NEWPATH;
