@@ -498,8 +498,10 @@ def strong_job(R: Ranks, width: int, height: int, spp: int, warmup: int, steps: 
     """A FIXED width x height x spp job split over the ranks (BASELINE's multi-GPU case).  Rank 0 gets the dict."""
     pt, objs, cam, tm = sharded_tracer(R, width, height, kernel)
     try:
-        pt.refresh()                     # untimed 1 spp pass: the specialised kernel of this resolution is built (NVRTC, ~2 s) and
-        pt.pathtrace(1)                  # the scratch buffer allocated before the clock starts, whatever `warmup` is
+        pt.refresh()                     # untimed short pass, whatever `warmup` is: the specialised kernel of this resolution is
+        pt.pathtrace(min(spp, 16))       # built (NVRTC, ~2 s), the per-sample scratch grows to its chunk size (4 GiB at 4096^2) and
+        if R.world > 1:                  # NCCL sets up its channels (first collective: ~0.3 s) before the clock starts
+            pt.reduce_tiles(0)
         pt.sync()
         t = timed_steps(R, pt, spp, warmup, steps)
         red = reduce_alone_ms(R, pt, spp)
@@ -738,5 +740,16 @@ def main() -> int:
     return 0
 
 
+def _only_json_on_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there as well (NCCL prints its version banner to stdout
+    when the box sets NCCL_DEBUG), so file descriptor 1 is pointed at stderr for the whole run and Python's sys.stdout keeps
+    a private copy of the original descriptor for the line itself."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(keep, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _only_json_on_stdout()
     sys.exit(main())
