@@ -151,3 +151,17 @@ def test_smooth_camera_easing_follows_reference_update():
     assert s.moving[None] == 0
     s.update(0.5, Cam)                                # velocity * dt > 1 clamps to 1
     np.testing.assert_allclose(s.position[None], [1, -0.2, 4], atol=1e-6)
+
+
+def test_bench_keeps_library_output_off_stdout():
+    """bench.py's contract is ONE JSON line on stdout; NCCL prints its version banner to file descriptor 1 when the box sets
+    NCCL_DEBUG.  After _only_json_on_stdout() raw writes to fd 1 land on stderr and only Python's prints reach stdout."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, bench; bench._only_json_on_stdout(); os.write(1, b'NCCL version x\\n'); "
+            "print('{\"metric\": 1}', flush=True)")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"metric": 1}\n'
+    assert "NCCL version x" in r.stderr
