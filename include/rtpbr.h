@@ -179,7 +179,10 @@ RTPBR_API int rtpbr_pathtrace(RtpbrContext* ctx, int spp);
 /* replaces kernel post_process() (src/postprocessor.py:24-43) / the tonemap tail of render()
  * (cornell_box_shortest.py:124-129).  mode: 0 family A, 1 family B, 2 family C, 3 v3. */
 RTPBR_API int rtpbr_post_process(RtpbrContext* ctx, int mode, float exposure, double gamma);  /* gamma in binary64: the
-   reference folds 1.0 / camera_gamma in Python before casting to f32 (src/postprocessor.py:32) */
+   reference folds 1.0 / camera_gamma in Python before casting to f32 (src/postprocessor.py:32).
+   Known divergences of this (f)-row pass, unlike the accumulation buffer, which is bit-exact: modes 0, 1 and 3 raise to the
+   gamma with the device's powf (within 2-3e-5 of the reference-source pixels, tests/test_golden.py; mode 2, the src/ order,
+   is bit-exact under the fp32 contract), and the NaN pixels cornell_box.py's tonemap produces for 0/0 are written as 0. */
 
 /* replaces kernel denoise(image_pixels, denoise_pixels, threshold) of examples/denoise/denoise_test_1.py:86-118 (the
  * temporal blend + bright-neighbour fill after shadertoy 7tKGzD) as an optional pass after rtpbr_post_process.  The
