@@ -507,7 +507,8 @@ inline Source generate(const RtpbrConfig& cfg, const RtpbrObject* objs, int n, i
     // as separate stages (pool_kernel.cuh), which needs the third form of the function (mode -1); the split keeps
     // ONE (need_mlp, pb) pair, so it is used for scenes with exactly one bunny
     // PBR families without the bunny: Philox and the normal's primitive switch out of line (code size, rt_math.cuh)
-    if (cfg.family != RTPBR_FAMILY_A && !bunny) s += "#define RT_RESOLVE_OOL 1\n";
+    const int ool = knob("RTPBR_RESOLVE_OOL");                    // tuning knob: -1 = automatic
+    if (ool == 1 || (ool < 0 && cfg.family != RTPBR_FAMILY_A && !bunny)) s += "#define RT_RESOLVE_OOL 1\n";
     const bool split = bunnies == 1 && cfg.marcher == RTPBR_MARCH_ENHANCED;
     if (split) s += "#define RT_JIT_SPLIT_BUNNY 1\n";
     s += "#include \"pool_kernel.cuh\"\nnamespace rt {\n";
