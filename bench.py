@@ -159,6 +159,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------ CPU legs
 CPU_BANDS, CPU_COLS, CPU_SPP = 32, 2, 64      # bounded CPU sample: 64 spread columns x 1024 rows x 64 spp = 4.19 M samples (~15 s)
+REF_BUDGET_S = 150.0                          # --impl reference: CPU seconds for all timed steps together (fewer columns per step for a large K)
 
 
 def cpu_sample_columns(width: int, bands: int = CPU_BANDS, cols: int = CPU_COLS):
@@ -198,17 +199,24 @@ def reference_arm(args, rank: int) -> int:
         return 0
     cores = cpu_threads()
     spp = CPU_SPP
+    rate = 0.0
     for _ in range(args.warmup):
-        run_cpu_oracle(1, hoisted=False, bands=4)
+        rate = max(rate, run_cpu_oracle(1, hoisted=False)[0])        # 64 columns x 1 spp: also calibrates the sample below
+    # bounded sample per step: the whole --steps K run stays within ~REF_BUDGET_S of CPU time whatever K is
+    bands = CPU_BANDS
+    if rate > 0.0:
+        fit = rate * 1e6 * (REF_BUDGET_S / args.steps) / (H * spp * CPU_COLS)      # bands that fit one step's share
+        while bands > 4 and bands > fit:
+            bands //= 2
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
-        v, n, dt = run_cpu_oracle(spp, hoisted=False)
+        v, n, dt = run_cpu_oracle(spp, hoisted=False, bands=bands)
         t_total += dt
         n_total += n
     value = n_total / t_total / 1e6
-    v_h, n_h, dt_h = run_cpu_oracle(spp, hoisted=True)
-    ncols = CPU_BANDS * CPU_COLS
-    sample = (f"{ncols} of {W} columns ({CPU_BANDS} spread bands x {CPU_COLS}) x {H} rows x {spp} spp = "
+    v_h, n_h, dt_h = run_cpu_oracle(spp, hoisted=True, bands=bands)
+    ncols = bands * CPU_COLS
+    sample = (f"{ncols} of {W} columns ({bands} spread bands x {CPU_COLS}) x {H} rows x {spp} spp = "
               f"{n_total // args.steps} samples per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
