@@ -380,7 +380,8 @@ int rtpbr_refresh(RtpbrContext* c)
 
 // Pool geometry and scheduling policy of an NVRTC build.  Environment knobs win; otherwise kernels with a fast region
 // (family A: short march step, small resolve phase) run 3 CTAs/SM x 88 slots per warp, regenerate paths (and continue
-// rays that dropped out of the region) in batches of their own and leave the march loop only when 6 lanes have finished
+// rays that dropped out of the region, and end the paths of rays that missed) in batches of their own -- when 28 slots
+// wait or 12 lanes idle -- and leave the march loop only when 6 lanes have finished
 // (profiles/r02_sweeps.md); everything else keeps
 // the ahead-of-time geometry.
 struct JitBuild {
@@ -404,7 +405,7 @@ static JitBuild jit_build_options(const rt::jit::Source& src)
     // 64 registers (tokyo_ibl +4.6 %, scene_demo +6 %, cornell_box_v3 +3.9 %, src +0.9 %; plain PBR marcher -1 %: stays at 4)
     b.min_blocks = env_int("RTPBR_POOL_MIN_BLOCKS", 1, 16, (src.fast || src.relaxed) ? 3 : rt::kPoolMinBlocks);
     const int regen_min = env_int("RTPBR_REGEN_MIN", 0, 32, src.fast ? 28 : 0);
-    const int regen_idle = env_int("RTPBR_REGEN_IDLE", 1, 32, src.fast ? 8 : 1);
+    const int regen_idle = env_int("RTPBR_REGEN_IDLE", 1, 32, src.fast ? 12 : 1);
     const int fin_min = env_int("RTPBR_FIN_MIN", 1, 32, src.fast ? 6 : 1);
     b.defs = { "-DRT_POOL_BLOCK=" + std::to_string(b.block), "-DRT_POOL_SLOTS=" + std::to_string(b.slots),
                "-DRT_POOL_MIN_BLOCKS=" + std::to_string(b.min_blocks) };

@@ -47,7 +47,8 @@ constexpr unsigned kFull = 0xffffffffu;
 //   RT_REGEN_MIN  RESOLVE splits into two batch types.  MODE_HITS batches shade hits / misses and start the next bounce:
 //                 no work-queue pulls, no new paths, no full-code march steps.  MODE_FRESH ("regeneration") batches
 //                 take the slots of the third stack, `fresh`: ended paths (fetch + camera ray + first roulette + the
-//                 camera ray's full-code steps towards the region) and ST_SLOW drop-outs.  They run when RT_REGEN_MIN
+//                 camera ray's full-code steps towards the region), ST_SLOW drop-outs and the rays that missed (their
+//                 path ends: sky colour, sample written, regeneration -- nothing of a hit batch).  They run when RT_REGEN_MIN
 //                 slots wait or RT_REGEN_IDLE lanes have nothing to march.
 //   RT_FIN_MIN    finished lanes wait (masked) until RT_FIN_MIN of them can leave the march loop together.
 // ------------------------------------------------------------------------------------------
@@ -220,7 +221,13 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
     for (;;) {
         const int st_in = st;
         if (MODE == MODE_FRESH) {
-            // regeneration batches carry no marched rays
+            // regeneration batches carry no hits; missed rays end their path here (they come straight from the march loop,
+            // or from slow_march() below) and the slot fetches a new path in the same pass
+            if (VAR::FAMILY != FAMILY_C && st == ST_MISS) {
+                if (VAR::COUNT) { cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
+                on_miss<VAR>(P, p);
+                st = ST_DONE;
+            }
         } else if (VAR::FAMILY != FAMILY_C) {
             if (st == ST_HIT) {
                 if (VAR::COUNT) { cnt.normals++; cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
@@ -361,7 +368,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
 #endif
             }
         }
-        const bool more = MODE == MODE_FRESH ? (st == ST_DONE || st == ST_FETCH)       // (irregular new rays go to the pending stack)
+        const bool more = MODE == MODE_FRESH ? (st == ST_DONE || st == ST_FETCH || st == ST_MISS)   // (hits of irregular new rays go to the pending stack)
                         : MODE == MODE_HITS  ? (st == ST_HIT || st == ST_MISS || st == ST_DONE)
                         : st == ST_HIT || st == ST_MISS || (VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE));
 #else
@@ -583,22 +590,23 @@ __device__ __forceinline__ void pool_body(const KParams& P)
             const bool mine = (fin >> lane) & 1u;
 #if defined(RT_JIT_FAST)
             const bool dropped = mine && march_undo_slow<VAR>(m, aux, slow);   // nothing was advanced: the march goes on in the resolve phase
-            // with regeneration batches the drop-outs wait for one of those (full-code steps at full lanes) instead of
-            // riding along in a hit batch
-            const unsigned drop_mask = kRegen ? __ballot_sync(kFull, dropped) : 0u;
 #else
             const bool dropped = false;
-            const unsigned drop_mask = 0u;
 #endif
+            const bool hit = mine && !dropped && march_status<VAR>(P, aux) == MARCH_HIT;
+            // with regeneration batches the drop-outs wait for one of those (full-code steps at full lanes) instead of
+            // riding along in a hit batch, and so do the missed rays: their path ends, all that is left to do is the
+            // regeneration, and the hit batches stay free of lanes that sit out the shading
+            const unsigned drop_mask = kRegen ? __ballot_sync(kFull, mine && !hit) : 0u;
             if (mine) {
                 const int r = __popc(fin & lane_lt);
                 if (dropped) {
                     store_parked<VAR, NSLOT>(pool, my, m);
                     pool.seti(F_STATUS, my, ST_SLOW);
                 } else {
-                    store_finished<VAR, NSLOT>(pool, my, m, march_status<VAR>(P, aux) == MARCH_HIT ? ST_HIT : ST_MISS);
+                    store_finished<VAR, NSLOT>(pool, my, m, hit ? ST_HIT : ST_MISS);
                 }
-                if (kRegen && dropped) fresh[n_fresh + __popc(drop_mask & lane_lt)] = (uint8_t)my;
+                if (kRegen && !hit) fresh[n_fresh + __popc(drop_mask & lane_lt)] = (uint8_t)my;
                 else pend[n_pend + __popc(fin & ~drop_mask & lane_lt)] = (uint8_t)my;
                 if (r < n_ready) {
                     my = ready[n_ready - 1 - r];
