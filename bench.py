@@ -30,7 +30,10 @@ What one JSON line carries
                 own bytes (16 B per sample of ordered-accumulation scratch) against MEASURED_PEAKS.json.
   cpu_baseline  the CPU oracle (oracle/oracle.c; stand-in for "Taichi ti.cpu", which cannot be installed here) on a
                 bounded sample of the same workload, all host threads.
-  --impl reference   the same CPU oracle as the reference arm (kind "port").
+  --impl reference   the same CPU oracle as the reference arm (kind "port"); the per-step sample shrinks for a large --steps so
+                that all timed steps fit ~150 s of CPU time (config.subsample says what was used).
+
+stdout carries exactly that one line: file descriptor 1 is pointed at stderr for the run (NCCL prints a version banner there).
 """
 from __future__ import annotations
 
