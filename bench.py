@@ -195,6 +195,17 @@ def cpu_threads() -> int:
         return os.cpu_count() or 1
 
 
+def reference_bands(rate_msamples: float, steps: int, spp: int = CPU_SPP) -> int:
+    """Column bands of one reference-arm step: CPU_BANDS, halved until `steps` steps at the calibrated rate fit REF_BUDGET_S
+    (never fewer than 4 bands = 8 columns)."""
+    bands = CPU_BANDS
+    if rate_msamples > 0.0:
+        fit = rate_msamples * 1e6 * (REF_BUDGET_S / max(steps, 1)) / (H * spp * CPU_COLS)      # bands that fit one step's share
+        while bands > 4 and bands > fit:
+            bands //= 2
+    return bands
+
+
 def reference_arm(args, rank: int) -> int:
     """--impl reference: the CPU stand-in for the reference's Taichi ti.cpu path (as-written:
     Euler matrices recomputed per object per march step, cornell_box_shortest.py:43)."""
@@ -206,11 +217,7 @@ def reference_arm(args, rank: int) -> int:
     for _ in range(args.warmup):
         rate = max(rate, run_cpu_oracle(1, hoisted=False)[0])        # 64 columns x 1 spp: also calibrates the sample below
     # bounded sample per step: the whole --steps K run stays within ~REF_BUDGET_S of CPU time whatever K is
-    bands = CPU_BANDS
-    if rate > 0.0:
-        fit = rate * 1e6 * (REF_BUDGET_S / args.steps) / (H * spp * CPU_COLS)      # bands that fit one step's share
-        while bands > 4 and bands > fit:
-            bands //= 2
+    bands = reference_bands(rate, args.steps, spp)
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
         v, n, dt = run_cpu_oracle(spp, hoisted=False, bands=bands)

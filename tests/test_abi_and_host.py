@@ -165,3 +165,20 @@ def test_bench_keeps_library_output_off_stdout():
     assert r.returncode == 0, r.stderr
     assert r.stdout == '{"metric": 1}\n'
     assert "NCCL version x" in r.stderr
+
+
+def test_bench_reference_arm_sample_fits_its_budget():
+    """--impl reference: the per-step sample shrinks with --steps so that all timed steps fit ~150 s of CPU time."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    per_band = bench.H * bench.CPU_SPP * bench.CPU_COLS / 1e6            # Msamples of one band
+    assert bench.reference_bands(0.30, 5) == bench.CPU_BANDS             # the GPU box's 16 cores, default K: the full 64 columns
+    assert bench.reference_bands(0.30, 20) == 16
+    assert bench.reference_bands(0.0, 20) == bench.CPU_BANDS             # no calibration: the default sample
+    for rate in (0.02, 0.07, 0.3, 1.0, 5.0):
+        for steps in (1, 2, 5, 20, 100):
+            b = bench.reference_bands(rate, steps)
+            assert 4 <= b <= bench.CPU_BANDS and (b & (b - 1)) == 0
+            assert b == 4 or b * per_band / rate * steps <= bench.REF_BUDGET_S * 1.0001
