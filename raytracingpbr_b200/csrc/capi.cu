@@ -412,6 +412,9 @@ static JitBuild jit_build_options(const rt::jit::Source& src)
     if (regen_min > 0) b.defs.push_back("-DRT_REGEN_MIN=" + std::to_string(regen_min));
     if (regen_idle > 1) b.defs.push_back("-DRT_REGEN_IDLE=" + std::to_string(regen_idle));
     if (fin_min > 1) b.defs.push_back("-DRT_FIN_MIN=" + std::to_string(fin_min));
+    if (const char* v = getenv("RTPBR_SLOW_FIRST")) {            // tuning knob: see pool_kernel.cuh RT_SLOW_FIRST
+        if (atoi(v) == 0) b.defs.push_back("-DRT_SLOW_FIRST=0");
+    }
     if (const char* v = getenv("RTPBR_MARCH_UNROLL")) {
         if (atoi(v) == 2) b.defs.push_back("-DRT_MARCH_VOTE_EVERY_2=1");
     }

@@ -175,6 +175,9 @@ enum : int { MODE_ALL = 0, MODE_HITS = 1, MODE_FRESH = 2 };
 #ifndef RT_FIN_MIN
 #define RT_FIN_MIN 1
 #endif
+#ifndef RT_SLOW_FIRST
+#define RT_SLOW_FIRST 1      // regeneration batches: full-code march steps at the top of the state machine (0: at its end, as before)
+#endif
 #ifndef RT_REGEN_IDLE
 #define RT_REGEN_IDLE 1      // regeneration batches also run when at least this many lanes have nothing to march
 #endif
@@ -219,10 +222,21 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
 
     // ---- run the slot's state machine until it needs marching again (or dies)
     for (;;) {
+        if (MODE == MODE_FRESH) {
+#if defined(RT_JIT_FAST) && RT_SLOW_FIRST
+            // Full-code march steps FIRST: the drop-outs of the march loop and the primary rays begun in the previous
+            // iteration (below) take them together, and a ray that turns out to have left the scene ends its path and is
+            // regenerated in THIS iteration, with everybody else -- not in an iteration of its own at a few lanes.
+            if (st == ST_SLOW) {
+                const int pre = slow_march<VAR>(P, p.m);
+                st = pre == MARCH_CONTINUE ? ST_READY : (pre == MARCH_HIT ? ST_HIT : ST_MISS);
+            }
+#endif
+        }
         const int st_in = st;
         if (MODE == MODE_FRESH) {
             // regeneration batches carry no hits; missed rays end their path here (they come straight from the march loop,
-            // or from slow_march() below) and the slot fetches a new path in the same pass
+            // or from slow_march()) and the slot fetches a new path in the same pass
             if (VAR::FAMILY != FAMILY_C && st == ST_MISS) {
                 if (VAR::COUNT) { cnt.rays++; cnt.evals += (unsigned long long)p.m.steps; }
                 on_miss<VAR>(P, p);
@@ -361,6 +375,8 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
                     // hit batches carry no full-code march steps and no region test: a bounce that begins outside the
                     // fast region (rare: bounces start on surfaces inside it) drops out of the march loop at its first
                     // step and then waits for a regeneration batch like every other drop-out
+                } else if (MODE == MODE_FRESH && RT_SLOW_FIRST) {
+                    st = ST_SLOW;                 // a new primary ray: its steps towards the region at the top of the next iteration
                 } else {
                     const int pre = slow_march<VAR>(P, p.m);
                     st = pre == MARCH_CONTINUE ? ST_READY : (pre == MARCH_HIT ? ST_HIT : ST_MISS);
@@ -368,7 +384,7 @@ __device__ __forceinline__ void resolve_batch(const KParams& P, Pool<NSLOT>& poo
 #endif
             }
         }
-        const bool more = MODE == MODE_FRESH ? (st == ST_DONE || st == ST_FETCH || st == ST_MISS)   // (hits of irregular new rays go to the pending stack)
+        const bool more = MODE == MODE_FRESH ? (st == ST_DONE || st == ST_FETCH || st == ST_MISS || (RT_SLOW_FIRST && st == ST_SLOW))   // (hits go to the pending stack)
                         : MODE == MODE_HITS  ? (st == ST_HIT || st == ST_MISS || st == ST_DONE)
                         : st == ST_HIT || st == ST_MISS || (VAR::FAMILY == FAMILY_C ? (st == ST_ADVANCE) : (st == ST_DONE));
 #else
